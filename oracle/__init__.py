@@ -1,0 +1,29 @@
+"""CPU oracle for the StreamingVLM hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This package is a CPU restatement (pure torch / numpy, no CUDA) of the reference's
+algorithm for the streaming-inference hot path.  Nothing in the product package
+(`streaming-vlm_b200/`) imports it; only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` do, and only as the checker or as
+the timed CPU baseline, never as the thing shipped.
+
+Parity status: PINNED for the integer / bf16-elementwise rows, by execution of the
+reference's own functions in the build container (`tests/golden/make_golden.py`
+exec's `get_qwen_range`, `prune_id_and_kv_cache`, `process_past_kv`, `get_rope_index`
+and `apply_multimodal_rotary_pos_emb` straight from `/root/reference/src` and commits
+their outputs as fixtures under `tests/golden/`).  The reference has no tests or golden
+vectors of its own.  The attention / ViT rows call
+flash-attn 2.8.3 in the reference and have no CPU implementation there; for those rows
+the oracle is the fp32 softmax(QK^T)V definition and parity is "unpinned" against the
+reference binary (tolerance stated in the tests).
+
+Module map (reference file:line each one follows is cited in the module docstrings):
+    tokens.py      get_qwen_range                      utils/get_qwen_range.py:15-86
+    eviction.py    prune / process_past_kv             inference/inference.py:50-172
+    cache.py       StreamingCache (list + torch.cat)   generate/streaming_cache.py:6-74
+    positions.py   get_rope_index, rotary tables, mRoPE qwen2_5/pos_emb.py:6-188,
+                                                       qwen2_5/language_forward.py:11-67
+    attention.py   LLM attention (prefill/decode)      qwen2_5/language_forward.py:143-260
+    vit.py         ViT encoder / attention / merger    qwen2_5/vision_forward.py:6-101
+    model.py       model forward + greedy streaming    qwen2_5/model_forward.py:30-176,
+                                                       inference/inference.py:309-517
+"""

@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures by EXECUTING THE REFERENCE'S OWN FUNCTIONS.
+
+Runs only in the build container (it reads /root/reference/src, which does not exist on
+the GPU box); the fixtures it writes next to this file are committed and are what the
+tests read.  Nothing is copied from the reference: its functions are loaded from their
+source files at run time, called on seeded synthetic inputs, and only their OUTPUTS are
+stored.
+
+    get_qwen_range                    imported as-is (utils/get_qwen_range.py)
+    prune_id_and_kv_cache,
+    contiguous_id_and_kv,
+    process_past_kv                   exec'd from the AST of inference/inference.py (the module
+                                      itself imports decord / qwen_vl_utils, absent here)
+    get_rope_index                    exec'd from qwen2_5/pos_emb.py with FPS = 2.0 injected
+                                      (qwen_vl_utils.vision_process.FPS of the pinned 0.0.11)
+    apply_multimodal_rotary_pos_emb   exec'd from qwen2_5/language_forward.py with HF's
+                                      `rotate_half` (same function in 4.52 and 5.5)
+
+Usage:  python tests/golden/make_golden.py
+"""
+import ast
+import hashlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/src"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from streaming_vlm.utils.get_qwen_range import TOKEN_IDS, get_qwen_range  # noqa: E402  (reference)
+from streaming_vlm_b200 import synthetic  # noqa: E402
+
+
+def _exec_functions(path, names, ns):
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(body) == len(names), (path, names)
+    exec(compile(ast.Module(body, []), path, "exec"), ns)
+    return ns
+
+
+class FakeCache:
+    """HF 4.52 DynamicCache surface used by inference.py: key_cache/value_cache lists,
+    iteration, get_seq_length.  Tensors are [1,1,S,1] holding arange(S), so that the
+    surviving values ARE the gather map."""
+
+    def __init__(self, n, layers=2):
+        self.key_cache = [torch.arange(n, dtype=torch.int64).view(1, 1, n, 1).clone() for _ in range(layers)]
+        self.value_cache = [torch.arange(n, dtype=torch.int64).view(1, 1, n, 1).clone() + 1000000 for _ in range(layers)]
+
+    def __iter__(self):
+        return iter(zip(self.key_cache, self.value_cache))
+
+    def get_seq_length(self):
+        return self.key_cache[0].shape[2]
+
+
+def rle(a):
+    """[(src_start, length), ...] of maximal +1 runs."""
+    runs = []
+    for x in a:
+        if runs and runs[-1][0] + runs[-1][1] == x:
+            runs[-1][1] += 1
+        else:
+            runs.append([int(x), 1])
+    return runs
+
+
+def sha(ids):
+    return hashlib.sha256(np.asarray(ids, dtype=np.int64).tobytes()).hexdigest()[:16]
+
+
+def simulate(ns, cfg):
+    """Drive process_past_kv exactly as streaming_inference does (inference.py:309-489) on a
+    synthetic stream; generated text is a seeded list of plain ids of variable length."""
+    rng = np.random.RandomState(cfg["seed"])
+    hist, clips, pixels = [], [], []
+    prev, cache = None, None
+    rounds = []
+    for i in range(cfg["rounds"]):
+        before = None if prev is None else prev.flatten().tolist()
+        if cache is not None:
+            cache = FakeCache(cache.get_seq_length())
+        cache, prev, clips, pixels = ns["process_past_kv"](
+            cache, i, text_round=cfg["text_round"], visual_round=cfg["window"], full_conversation_history=hist,
+            prev_generated_ids=prev, assistant_start_bias=3, assistant_end_bias=2, recent_video_window_clips=clips,
+            recent_pixel_values_videos=pixels, text_sink=cfg["text_sink"], text_sliding_window=cfg["text_sliding_window"])
+        rec = {"i": i}
+        if before is not None:
+            g = cache.key_cache[0][0, 0, :, 0].tolist()
+            assert cache.value_cache[1][0, 0, :, 0].tolist() == [x + 1000000 for x in g]
+            rec.update(before_len=len(before), before_sha=sha(before), after_ids_sha=sha(prev.flatten().tolist()),
+                       after_len=int(prev.shape[1]), cache_runs=rle(g))
+            if i in cfg.get("dump_rounds", ()):
+                rec["after_ids"] = prev.flatten().tolist()
+        rounds.append(rec)
+        clips.append(None)
+        prompt = synthetic.round_prompt(i, cfg["n_vis"], cfg["prev_text"], 8, cfg["seed"])
+        if i == 0:
+            hist[:] = [{"role": "previous text", "content": "p" * 10},
+                       {"role": "user", "content": [{"type": "text", "text": "T"}, {"type": "video"}, {"type": "text", "text": "q"}]}]
+        else:
+            hist.append({"role": "user", "content": [{"type": "text", "text": "T"}, {"type": "video"}]})
+        ids = prompt if prev is None else (prev.flatten().tolist() + (prompt if prev[0, -1].item() != 198 else prompt[1:]))
+        pixels.append(None)
+        input_len = len(ids)
+        n_new = int(rng.randint(cfg["gen_lo"], cfg["gen_hi"] + 1))
+        eos = bool(rng.rand() < cfg["p_eos"])
+        gen = rng.randint(1000, 100000, size=n_new).tolist()
+        gen = [g if g not in (872, 77091, 1462, 198, 19702, 1467) else 1000 for g in gen]
+        if eos:
+            gen[-1] = 151645
+        seq = ids + gen
+        cache_len = len(seq) - 1                   # the last sampled token is never fed back
+        if seq[-1] != 151645:
+            seq = seq + [151645]                   # inference.py:457-459
+        prev = torch.tensor([seq], dtype=torch.long)
+        cache = FakeCache(cache_len)
+        hist.append({"role": "assistant", "content": "x" * 8 + " ..."})
+        rec["input_len"] = input_len
+        rec["gen"] = gen
+    return rounds
+
+
+def main():
+    ns = {"torch": torch, "get_qwen_range": get_qwen_range, "TOKEN_IDS": TOKEN_IDS, "breakpoint": lambda: (_ for _ in ()).throw(RuntimeError("breakpoint"))}
+    _exec_functions(f"{REF}/streaming_vlm/inference/inference.py",
+                    ["prune_id_and_kv_cache", "contiguous_id_and_kv", "process_past_kv"], ns)
+
+    # ---------------------------------------------------------------- eviction streams
+    configs = [
+        dict(name="default_16_16_512_512", window=16, text_round=16, text_sink=512, text_sliding_window=512, rounds=150,
+             n_vis=256, prev_text=24, gen_lo=4, gen_hi=20, p_eos=0.5, seed=1, dump_rounds=[16, 17, 149]),
+        dict(name="small_4_4_16_24", window=4, text_round=4, text_sink=16, text_sliding_window=24, rounds=40,
+             n_vis=16, prev_text=6, gen_lo=3, gen_hi=9, p_eos=0.5, seed=2, dump_rounds=[4, 5, 20, 39]),
+        dict(name="vis_gt_text_6_3_8_8", window=6, text_round=3, text_sink=8, text_sliding_window=8, rounds=30,
+             n_vis=16, prev_text=4, gen_lo=3, gen_hi=9, p_eos=0.3, seed=3, dump_rounds=[6, 29]),
+        dict(name="text_gt_vis_3_6_8_8", window=3, text_round=6, text_sink=8, text_sliding_window=8, rounds=30,
+             n_vis=16, prev_text=4, gen_lo=3, gen_hi=9, p_eos=0.3, seed=4, dump_rounds=[6, 29]),
+        dict(name="no_trim_4_4_none", window=4, text_round=4, text_sink=None, text_sliding_window=None, rounds=20,
+             n_vis=16, prev_text=4, gen_lo=3, gen_hi=6, p_eos=1.0, seed=5, dump_rounds=[19]),
+    ]
+    out = []
+    for cfg in configs:
+        rounds = simulate(ns, cfg)
+        out.append({"config": cfg, "rounds": rounds})
+        last = rounds[-1]
+        print(cfg["name"], "last before/after", last.get("before_len"), last.get("after_len"), "runs", last.get("cache_runs"))
+    json.dump(out, open(os.path.join(HERE, "eviction_streams.json"), "w"))
+
+    # ---------------------------------------------------------------- get_qwen_range probes
+    probes = []
+    for cfg_i, item in enumerate(out[:4]):
+        for rec in item["rounds"]:
+            if "after_ids" not in rec:
+                continue
+            ids = rec["after_ids"]
+            for label in ["user", "previous text", "assistant", "vision", "user_text"]:
+                for idx in [0, 1, -1, -2]:
+                    for lf in [True, False]:
+                        try:
+                            r = list(get_qwen_range(torch.tensor([ids]), label, idx, contain_lf=lf))
+                        except IndexError:
+                            r = None
+                        probes.append({"stream": cfg_i, "round": rec["i"], "label": label, "index": idx, "contain_lf": lf, "range": r})
+    # adversarial: unterminated segment, adjacent patterns, lf at the very end
+    adv = [
+        [151644, 872, 198, 5, 6, 151645, 198, 151644, 872, 198, 7],
+        [151644, 77091, 198, 151645, 151644, 77091, 198, 9, 151645, 198],
+        [151652, 151656, 151656, 151653, 151652, 151653],
+        [1462, 3, 4, 151652, 151656, 151653, 1462, 151652],
+        [151644, 19702, 1467, 198, 151645],
+        [5, 6, 7],
+    ]
+    for a_i, ids in enumerate(adv):
+        for label in ["user", "previous text", "assistant", "vision", "user_text"]:
+            for idx in [0, 1, -1]:
+                for lf in [True, False]:
+                    try:
+                        r = list(get_qwen_range(torch.tensor([ids]), label, idx, contain_lf=lf))
+                    except IndexError:
+                        r = None
+                    probes.append({"adv": a_i, "ids": ids, "label": label, "index": idx, "contain_lf": lf, "range": r})
+    json.dump(probes, open(os.path.join(HERE, "qwen_range_probes.json"), "w"))
+    print("range probes", len(probes))
+
+    # ---------------------------------------------------------------- get_rope_index
+    stub = types.ModuleType("qwen_vl_utils"); vp = types.ModuleType("qwen_vl_utils.vision_process"); vp.FPS = 2.0
+    ns2 = {"torch": torch, "Optional": __import__("typing").Optional, "Tuple": __import__("typing").Tuple, "FPS": 2.0}
+    _exec_functions(f"{REF}/streaming_vlm/inference/qwen2_5/pos_emb.py", ["get_rope_index"], ns2)
+
+    class _Cfg:  # the attributes get_rope_index reads (pos_emb.py:45-48, :126)
+        class vision_config:
+            spatial_merge_size = 2
+            tokens_per_second = 2
+        image_token_id = 151655
+        video_token_id = 151656
+        vision_start_token_id = 151652
+    self_stub = types.SimpleNamespace(config=_Cfg)
+    rope = {}
+    cases = []
+    for item in out[:4]:
+        cfg = item["config"]
+        for rec in item["rounds"]:
+            if "after_ids" in rec:
+                side = int(round(cfg["n_vis"] ** 0.5)) * 2
+                cases.append((rec["after_ids"], [1, side, side], f"{cfg['name']}_r{rec['i']}"))
+    # extra: multi-frame grid (t=2), non-square grid, trailing zeros as in decode steps
+    ids_t2 = synthetic.SYSTEM_PROMPT + [151644, 872, 198, 1462, 5, 151652] + [151656] * (2 * 2 * 3) + [151653, 151645, 198, 7, 8, 0, 0, 0]
+    cases.append((ids_t2, [2, 4, 6], "t2_h2_w3_trailing_zeros"))
+    for ids, grid, name in cases:
+        t = torch.tensor([ids], dtype=torch.long)
+        nvid = int((t == 151656).sum().item() // max(1, (grid[0] * (grid[1] // 2) * (grid[2] // 2))))
+        g = torch.tensor([grid] * (nvid + 3), dtype=torch.long)   # grid list longer than needed, as in the reference (:415)
+        pos, delta = ns2["get_rope_index"](self_stub, t, None, g, None, torch.ones_like(t, dtype=torch.bool))
+        rope[name + "__ids"] = np.asarray(ids, dtype=np.int64)
+        rope[name + "__grid"] = np.asarray(grid, dtype=np.int64)
+        rope[name + "__pos"] = pos.numpy()
+        rope[name + "__delta"] = np.asarray(delta.numpy())
+        print("rope", name, pos.shape, float(pos.max()))
+    np.savez_compressed(os.path.join(HERE, "rope_index.npz"), **rope)
+
+    # ---------------------------------------------------------------- mRoPE apply (bf16 op order)
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VLRotaryEmbedding, rotate_half
+    ns3 = {"torch": torch, "rotate_half": rotate_half}
+    _exec_functions(f"{REF}/streaming_vlm/inference/qwen2_5/language_forward.py", ["apply_multimodal_rotary_pos_emb"], ns3)
+    g = torch.Generator().manual_seed(11)
+    name = "default_16_16_512_512_r17"
+    pos = torch.from_numpy(rope[name + "__pos"])[:, :, :700]
+    inv_freq = 1.0 / (1e6 ** (torch.arange(0, 128, 2, dtype=torch.int64).to(torch.float32) / 128))
+    # HF rotary forward (modeling_qwen2_5_vl.py:595-608), inlined because the module wants a config object
+    freqs = (inv_freq[None, None, :, None].float().expand(3, 1, -1, 1) @ pos[:, :, None, :].float()).transpose(2, 3)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    cos, sin = emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
+    q = torch.randn(1, 4, 37, 128, generator=g).to(torch.bfloat16)
+    k = torch.randn(1, 2, 700, 128, generator=g).to(torch.bfloat16)
+    qe, ke = ns3["apply_multimodal_rotary_pos_emb"](q, k, cos, sin, [16, 24, 24])
+    np.savez_compressed(os.path.join(HERE, "mrope_apply.npz"), pos=pos.numpy(),
+                        q=q.view(torch.int16).numpy(), k=k.view(torch.int16).numpy(),
+                        cos=cos.view(torch.int16).numpy(), sin=sin.view(torch.int16).numpy(),
+                        q_rot=qe.view(torch.int16).numpy(), k_rot=ke.view(torch.int16).numpy())
+    print("mrope", qe.shape, ke.shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""CPU: pin the oracle against fixtures produced by executing the reference's own
+functions (tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eviction, positions, tokens
+from oracle.cache import ListCache
+from tests.stream_sim import replay, rle, sha
+
+
+def _tagged(n, layers=2):
+    c = ListCache()
+    for li in range(layers):
+        c.key_cache.append(torch.arange(n, dtype=torch.int64).view(1, 1, n, 1).clone())
+        c.value_cache.append(torch.arange(n, dtype=torch.int64).view(1, 1, n, 1) + 1000000)
+    return c
+
+
+@pytest.fixture(scope="module")
+def streams(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "eviction_streams.json")))
+
+
+def test_get_qwen_range_matches_reference(golden_dir, streams):
+    probes = json.load(open(os.path.join(golden_dir, "qwen_range_probes.json")))
+    assert len(probes) > 500
+    by_round = {(si, r["i"]): r["after_ids"] for si, item in enumerate(streams) for r in item["rounds"] if "after_ids" in r}
+    for p in probes:
+        ids = p["ids"] if "adv" in p else by_round[(p["stream"], p["round"])]
+        try:
+            got = list(tokens.get_qwen_range(ids, p["label"], p["index"], p["contain_lf"]))
+        except IndexError:
+            got = None
+        assert got == p["range"], p
+
+
+@pytest.mark.parametrize("si", range(5))
+def test_process_past_kv_matches_reference(streams, si):
+    item = streams[si]
+    cfg = item["config"]
+    n = 0
+    for rec, before, after, gather in replay(eviction.process_past_kv, _tagged,
+                                             lambda c: c.key_cache[0][0, 0, :, 0].tolist(), cfg, item["rounds"]):
+        assert len(before) == rec["before_len"] and sha(before) == rec["before_sha"]
+        assert len(after) == rec["after_len"], (cfg["name"], rec["i"])
+        assert sha(after) == rec["after_ids_sha"], (cfg["name"], rec["i"])
+        assert rle(gather) == rec["cache_runs"], (cfg["name"], rec["i"])
+        if "after_ids" in rec:
+            assert after == rec["after_ids"]
+        n += 1
+    assert n == cfg["rounds"] - 1
+
+
+def test_steady_state_is_five_runs(streams):
+    """defaults 16/16/512/512 settle into a 5-run gather."""
+    last = streams[0]["rounds"][-1]
+    assert len(last["cache_runs"]) == 5
+    assert last["cache_runs"][0] == [0, 527]
+
+
+def test_get_rope_index_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rope_index.npz"))
+    names = sorted({k.split("__")[0] for k in z.files})
+    assert len(names) >= 10
+    for nme in names:
+        ids, grid, ref = z[nme + "__ids"], z[nme + "__grid"], z[nme + "__pos"]
+        pos, delta = positions.get_rope_index(ids, [grid.tolist()] * 64)
+        assert pos.dtype == torch.float32 and tuple(pos.shape) == ref.shape
+        assert np.array_equal(pos.numpy(), ref), nme
+        assert delta == int(z[nme + "__delta"].reshape(-1)[0]), nme
+
+
+def test_mrope_apply_bit_exact(golden_dir):
+    z = np.load(os.path.join(golden_dir, "mrope_apply.npz"))
+    bf = lambda a: torch.from_numpy(a).view(torch.bfloat16)
+    pos = torch.from_numpy(z["pos"])
+    cos, sin = positions.rotary_cos_sin(pos, positions.default_inv_freq(128, 1e6))
+    assert torch.equal(cos.view(torch.int16), torch.from_numpy(z["cos"]))
+    assert torch.equal(sin.view(torch.int16), torch.from_numpy(z["sin"]))
+    q_rot, k_rot = positions.apply_mrope(bf(z["q"]), bf(z["k"]), cos, sin)
+    assert torch.equal(q_rot.view(torch.int16), torch.from_numpy(z["q_rot"]))
+    assert torch.equal(k_rot.view(torch.int16), torch.from_numpy(z["k_rot"]))
+
+
+def test_rotary_table_equals_per_position_embedding(golden_dir):
+    """The integer-position table the CUDA path indexes is the same numbers HF's rotary
+    module produces for those positions."""
+    z = np.load(os.path.join(golden_dir, "mrope_apply.npz"))
+    pos = torch.from_numpy(z["pos"])                       # [3,1,S], integer valued
+    inv = positions.default_inv_freq(128, 1e6)
+    cos, sin = positions.rotary_cos_sin(pos, inv)
+    tc, ts = positions.rotary_table(int(pos.max()) + 1, inv)
+    for ax in range(3):
+        idx = pos[ax, 0].long()
+        assert torch.equal(tc[idx].view(torch.int16), cos[ax, 0, :, :64].view(torch.int16))
+        assert torch.equal(ts[idx].view(torch.int16), sin[ax, 0, :, 64:].view(torch.int16))
