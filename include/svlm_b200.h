@@ -1,0 +1,173 @@
+/*
+ * svlm_b200.h -- C ABI of the B200-native (sm_100a) StreamingVLM hot path.
+ *
+ * The reference (rahim-xelpmoc/streaming-vlm) is pure Python and has no FFI: its "operator
+ * interface" for this path is a set of Python call sites that invoke torch / flash-attn
+ * kernels.  Each entry point below replaces one of those call sites (cited as
+ * file:line relative to the reference's src/streaming_vlm/) and is what a torch custom-op
+ * / ctypes layer binds.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every `const void*` / `void*` tensor argument is a DEVICE pointer unless the name ends
+ *     in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - all kernels are asynchronous on `stream`, allocate nothing, never synchronise, and are
+ *     CUDA-graph capturable; bf16 tensors are raw `uint16_t` bit patterns;
+ *   - return value: 0 on success, a negative SVLM_E* code otherwise; `svlm_last_error()`
+ *     returns a thread-local, human-readable message for the last failure;
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry
+ *     point returns SVLM_ENODEV.
+ *
+ * KV arena (one per video stream, owned by the caller, e.g. a torch tensor):
+ *   bf16 [2 buffers][3 planes][L layers][H_kv][cap tokens][D]
+ *   plane 0 = K_raw (un-rotated keys, the reference's cache content in shrink mode),
+ *   plane 1 = K_rot (keys rotated at their current contiguous positions),
+ *   plane 2 = V.
+ *   Compaction ping-pongs between the two buffers (source and destination never alias).
+ */
+#ifndef SVLM_B200_H_
+#define SVLM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVLM_OK        0
+#define SVLM_EINVAL   -1   /* bad argument (shape, alignment, capacity, too many runs ...) */
+#define SVLM_ECUDA    -2   /* a CUDA runtime / driver call failed */
+#define SVLM_ENODEV   -3   /* no sm_100 device / driver entry point unavailable */
+
+#define SVLM_MAX_RUNS 32   /* maximum number of gather runs per compaction launch */
+
+#define SVLM_PLANE_K_RAW 0
+#define SVLM_PLANE_K_ROT 1
+#define SVLM_PLANE_V     2
+
+int         svlm_version(void);          /* ABI version, currently 1 */
+const char* svlm_last_error(void);
+
+/* Description of one stream's arena; strides follow from the dense layout above. */
+typedef struct {
+    void*   base;        /* device pointer to buffer 0, plane 0 */
+    int32_t layers;      /* L */
+    int32_t kv_heads;    /* H_kv */
+    int32_t head_dim;    /* D (128) */
+    int32_t capacity;    /* cap: tokens per (layer, head) plane */
+} svlm_arena_t;
+
+/* ---------------------------------------------------------------------------------------
+ * (1) KV-cache compaction fused with the contiguous-RoPE re-rotation.
+ * Replaces: inference/inference.py:50-61 (prune_id_and_kv_cache: index_select per layer),
+ *           :100-108 (resort_id_and_kv: torch.cat), :63-68 (contiguous_id_and_kv), i.e. every
+ *           full-cache copy process_past_kv (:87-172) makes in one chunk, AND the per-forward
+ *           re-rotation of the whole cached K, qwen2_5/language_forward.py:58-66, for the
+ *           retained tokens.
+ * The gather is given as `n_runs` runs (src_start, dst_start, length), all layers / heads /
+ * planes in ONE launch: dst[plane][l][h][dst_start+i] = src[plane][l][h][src_start+i] for
+ * K_raw and V (bit-exact copy), and K_rot[dst] = mrope(K_raw[src], pos[:, dst]) with the
+ * reference's bf16 rounding order (x*cos and rot(x)*sin each rounded, then the sum).
+ *   runs_host   : host pointer, int32 [n_runs][3]
+ *   src_buffer  : 0 or 1; the destination is the other buffer
+ *   pos         : int32 [3][pos_stride] contiguous mRoPE positions of the DESTINATION tokens
+ *   cos_table / sin_table : bf16 [table_rows][D/2]; row p = cos/sin(p * inv_freq) rounded once
+ *   mrope_section : int32 [3], e.g. {16,24,24}; every section must be a multiple of 8
+ * ------------------------------------------------------------------------------------- */
+int svlm_kv_compact_rope(const svlm_arena_t* arena, int src_buffer, const int32_t* runs_host, int n_runs,
+                         const int32_t* pos, int pos_stride, const void* cos_table, const void* sin_table,
+                         int table_rows, const int32_t* mrope_section_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) Contiguous 3-D mRoPE position ids of a pruned id sequence.
+ * Replaces: qwen2_5/pos_emb.py:6-188 (get_rope_index) as called in shrink mode by
+ *           qwen2_5/model_forward.py:101-110 (full ids, image_grid_thw=None, mask of ones).
+ *   ids        : int64 [n] device
+ *   grids_thw  : int32 [n_grids][3] device, consumed from index 0 in block order
+ *   t_step     : (2 / FPS) * tokens_per_second as an integer (2 for the pinned versions)
+ *   pos_out    : int32 [3][pos_stride]; integer-valued, equal to the reference's float32 ids
+ *   next_pos_out : int32 [1] = max position + 1 (first position of a token appended later)
+ *   status_out : int32 [1], set non-zero if a run of video tokens does not match its grid
+ * ------------------------------------------------------------------------------------- */
+int svlm_mrope_positions(const int64_t* ids, int n, const int32_t* grids_thw, int n_grids, int spatial_merge,
+                         int t_step, int64_t video_token_id, int32_t* pos_out, int pos_stride,
+                         int32_t* next_pos_out, int32_t* status_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) Append new tokens: rotate q, write K_raw / K_rot / V rows into the arena.
+ * Replaces: generate/streaming_cache.py:72-73 (torch.cat append per layer per forward) and
+ *           qwen2_5/language_forward.py:47-56, :64-66 (mRoPE of q, right aligned, and of
+ *           the new keys).
+ *   q / k / v  : bf16, token-major; element (t, head, d) at t*row_stride + head*D + d
+ *   q_out      : bf16 [T][Hq][D] rotated queries
+ *   start      : arena row of the first new token; if start_dev != NULL the kernel reads it
+ *                from device memory instead (graph-replayable decode)
+ *   pos        : int32 [3][pos_stride]; the token at arena row r uses pos[:, r].
+ *                If text_pos_dev != NULL (decode), token t instead takes the scalar
+ *                *text_pos_dev + t on all three axes (plain text continuation).
+ * ------------------------------------------------------------------------------------- */
+int svlm_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, const void* q, const void* k,
+                         const void* v, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
+                         int n_tokens, int q_heads, void* q_out, int start, const int32_t* start_dev,
+                         const int32_t* pos, int pos_stride, const int32_t* text_pos_dev,
+                         const void* cos_table, const void* sin_table, int table_rows,
+                         const int32_t* mrope_section_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (4) Causal GQA attention over the arena: chunk prefill (Tq > 1) and decode (Tq = 1).
+ * Replaces: qwen2_5/language_forward.py:199-252 (repeat_kv + _flash_attention_forward ->
+ *           flash_attn_func, causal, bottom-right aligned, scale 1/sqrt(D)).
+ * tcgen05 (UMMA) QK^T and PV with TMEM accumulators, TMA-staged K/V tiles, online softmax.
+ *   q          : bf16 [Tq][Hq][D] (rotated), out: bf16 [Tq][Hq][D]
+ *   kv_len     : number of valid arena rows INCLUDING the Tq new tokens; if kv_len_dev != NULL
+ *                it is read from device memory (kv_len then is an upper bound used for the grid)
+ *   num_splits : >= 1; with > 1 the KV range is split across CTAs and merged by a second
+ *                kernel.  workspace: fp32, svlm_attn_workspace_bytes(...) bytes.
+ * ------------------------------------------------------------------------------------- */
+size_t svlm_attn_workspace_bytes(int n_q_tokens, int q_heads, int head_dim, int num_splits);
+int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int n_q_tokens,
+                     int q_heads, int kv_len, const int32_t* kv_len_dev, int num_splits, void* workspace,
+                     size_t workspace_bytes, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (5) ViT attention: 2-D RoPE + packed variable-length non-causal attention.
+ * Replaces: qwen2_5/vision_forward.py:28 (apply_rotary_pos_emb_flashatt) and :32-35
+ *           (flash_attn_varlen_func with cu_seqlens = windows or whole frames).
+ *   qkv        : bf16 [N][3][H][D] (output of the fused qkv Linear); q and k are rotated IN
+ *                PLACE by svlm_vit_rope, then read by svlm_vit_attn through TMA
+ *   cos / sin  : fp32 [N][D] (the reference's position_embeddings after window reordering)
+ *   cu_seqlens : int32 [n_seqs + 1] device, ascending, last = N
+ *   out        : bf16 [N][H][D]
+ * ------------------------------------------------------------------------------------- */
+int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int n_tokens, int heads, int head_dim,
+                  void* stream);
+int svlm_vit_attn(const void* qkv, const int32_t* cu_seqlens, int n_seqs, void* out, int n_tokens, int heads,
+                  int head_dim, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (6) Dense bf16 GEMM with fused epilogue, C = act(A * W^T + bias), on tcgen05 / TMA.
+ * Replaces: HF Qwen2_5_VLPatchMerger.forward as called at qwen2_5/vision_forward.py:98
+ *           (Linear + GELU(erf) + Linear; the RMSNorm prologue is svlm_rmsnorm and the
+ *           `argsort(window_index)` un-permute of :99 is the optional row scatter).
+ *   A [M][K] bf16 row-major, W [N][K] bf16 row-major (nn.Linear layout), bias [N] bf16 or NULL
+ *   act        : 0 = none, 1 = GELU(erf)
+ *   out_rows   : int32 [M] or NULL; row m of the result is stored at row out_rows[m] of C
+ * ------------------------------------------------------------------------------------- */
+int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int M, int N, int K, int act,
+                   const int32_t* out_rows, void* stream);
+int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (the reference-facing plugin call with HOST data):
+ * copy in, run, copy out, synchronise.  Used by bench.py's end-to-end leg and by callers that
+ * keep the cache in host memory.
+ * ------------------------------------------------------------------------------------- */
+int svlm_kv_compact_rope_host(void* arena_host, int layers, int kv_heads, int head_dim, int capacity,
+                              int src_buffer, const int32_t* runs_host, int n_runs, const int32_t* pos_host,
+                              int pos_stride, const void* cos_table_host, const void* sin_table_host,
+                              int table_rows, const int32_t* mrope_section_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVLM_B200_H_ */

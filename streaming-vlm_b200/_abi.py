@@ -1,0 +1,264 @@
+"""ctypes binding of the C ABI (`include/svlm_b200.h`) and the `svlm::*` torch custom ops.
+
+The shared library is built in-tree by `build()` (plain `nvcc -shared`, sm_100a only, no torch
+headers) and loaded with ctypes; tensors cross the boundary as raw device pointers plus the
+current CUDA stream.  There is no fallback: if the library is missing or an entry point returns
+an error code, a RuntimeError with the library's message is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libsvlm_b200.so")
+SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "gemm.cu"]
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "svlm_b200.h")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
+           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
+           "svlm_rmsnorm", "svlm_kv_compact_rope_host"]
+
+MAX_RUNS = 32
+
+
+class Arena(Structure):
+    _fields_ = [("base", c_void_p), ("layers", c_int32), ("kv_heads", c_int32), ("head_dim", c_int32),
+                ("capacity", c_int32)]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.join(_CSRC, "common.cuh"), HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libsvlm_b200.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    r = subprocess.run(cmd, cwd=_CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library (no compute is attempted here, so this also works on a CPU-only box)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first. "
+                           "There is no CPU / PyTorch fallback for this path.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32p = c_void_p, POINTER(c_int32)
+    L.svlm_version.restype = c_int
+    L.svlm_last_error.restype = c_char_p
+    L.svlm_kv_compact_rope.argtypes = [POINTER(Arena), c_int, i32p, c_int, vp, c_int, vp, vp, c_int, i32p, vp]
+    L.svlm_mrope_positions.argtypes = [vp, c_int, vp, c_int, c_int, c_int, c_int64, vp, c_int, vp, vp, vp]
+    L.svlm_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int, c_int, vp,
+                                       c_int, vp, vp, c_int, vp, vp, vp, c_int, i32p, vp]
+    L.svlm_attn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    L.svlm_attn_workspace_bytes.restype = c_size_t
+    L.svlm_attn_causal.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, vp, c_size_t, c_float, vp]
+    L.svlm_vit_rope.argtypes = [vp, vp, vp, c_int, c_int, c_int, vp]
+    L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
+    L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
+    L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
+    L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("svlm_last_error", "svlm_attn_workspace_bytes", "svlm_version"):
+            fn.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().svlm_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("svlm ops run on CUDA tensors only (no CPU fallback)")
+
+
+def i32_array(vals):
+    return (c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+class ArenaView:
+    """A torch bf16 tensor [2, 3, L, H, cap, D] described for the C ABI."""
+
+    def __init__(self, tensor: torch.Tensor):
+        assert tensor.dtype == torch.bfloat16 and tensor.dim() == 6 and tensor.shape[0] == 2 and tensor.shape[1] == 3
+        assert tensor.is_contiguous()
+        _req_cuda(tensor)
+        self.tensor = tensor
+        _, _, self.layers, self.kv_heads, self.capacity, self.head_dim = tensor.shape
+        self.c = Arena(tensor.data_ptr(), self.layers, self.kv_heads, self.head_dim, self.capacity)
+        self.ref = ctypes.byref(self.c)
+
+
+# ------------------------------------------------------------------------------------------------
+# Thin functional wrappers (raw fast path used by the engine)
+# ------------------------------------------------------------------------------------------------
+def kv_compact_rope(arena: ArenaView, src_buffer: int, runs, pos: torch.Tensor, cos_table, sin_table, section):
+    """runs: list of (src_start, dst_start, length)."""
+    _req_cuda(pos, cos_table, sin_table)
+    flat = [x for r in runs for x in r]
+    check(lib().svlm_kv_compact_rope(arena.ref, src_buffer, i32_array(flat), len(runs), pos.data_ptr(), pos.stride(0),
+                                     cos_table.data_ptr(), sin_table.data_ptr(), cos_table.shape[0], i32_array(section),
+                                     _stream()), "svlm_kv_compact_rope")
+
+
+def mrope_positions(ids: torch.Tensor, n: int, grids: torch.Tensor, n_grids: int, pos: torch.Tensor, next_pos: torch.Tensor,
+                    status: torch.Tensor, spatial_merge: int = 2, t_step: int = 2, video_token_id: int = 151656):
+    _req_cuda(ids, grids, pos, next_pos, status)
+    assert ids.dtype == torch.int64 and pos.dtype == torch.int32 and grids.dtype == torch.int32
+    check(lib().svlm_mrope_positions(ids.data_ptr(), n, grids.data_ptr(), n_grids, spatial_merge, t_step, video_token_id,
+                                     pos.data_ptr(), pos.stride(0), next_pos.data_ptr(), status.data_ptr(), _stream()),
+          "svlm_mrope_positions")
+
+
+def qkv_rope_append(arena: ArenaView, buffer: int, layer: int, q, k, v, n_tokens: int, q_heads: int, q_out, start: int, pos,
+                    cos_table, sin_table, section, start_dev=None, text_pos_dev=None):
+    _req_cuda(q, k, v, q_out)
+    check(lib().svlm_qkv_rope_append(arena.ref, buffer, layer, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0),
+                                     v.stride(0), n_tokens, q_heads, q_out.data_ptr(), start, _ptr(start_dev), _ptr(pos),
+                                     0 if pos is None else pos.stride(0), _ptr(text_pos_dev), cos_table.data_ptr(),
+                                     sin_table.data_ptr(), cos_table.shape[0], i32_array(section), _stream()),
+          "svlm_qkv_rope_append")
+
+
+def attn_workspace_bytes(n_q_tokens: int, q_heads: int, head_dim: int, num_splits: int) -> int:
+    return int(lib().svlm_attn_workspace_bytes(n_q_tokens, q_heads, head_dim, num_splits))
+
+
+def attn_causal(arena: ArenaView, buffer: int, layer: int, q, out, n_q_tokens: int, q_heads: int, kv_len: int, scale: float,
+                num_splits: int = 1, workspace=None, kv_len_dev=None):
+    _req_cuda(q, out)
+    check(lib().svlm_attn_causal(arena.ref, buffer, layer, q.data_ptr(), out.data_ptr(), n_q_tokens, q_heads, kv_len,
+                                 _ptr(kv_len_dev), num_splits, _ptr(workspace),
+                                 0 if workspace is None else workspace.numel() * workspace.element_size(), scale, _stream()),
+          "svlm_attn_causal")
+
+
+def vit_rope(qkv, cos, sin, n_tokens: int, heads: int, head_dim: int):
+    _req_cuda(qkv, cos, sin)
+    assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+    check(lib().svlm_vit_rope(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), n_tokens, heads, head_dim, _stream()), "svlm_vit_rope")
+
+
+def vit_attn(qkv, cu_seqlens, out, n_tokens: int, heads: int, head_dim: int, scale: float):
+    _req_cuda(qkv, cu_seqlens, out)
+    assert cu_seqlens.dtype == torch.int32
+    check(lib().svlm_vit_attn(qkv.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, out.data_ptr(), n_tokens, heads,
+                              head_dim, scale, _stream()), "svlm_vit_attn")
+
+
+def gemm_bf16(a, w, bias, out, act: int = 0, out_rows=None):
+    _req_cuda(a, w, out)
+    m, k = a.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and a.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    check(lib().svlm_gemm_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k, act, _ptr(out_rows), _stream()),
+          "svlm_gemm_bf16")
+
+
+def rmsnorm(x, weight, out, eps: float):
+    _req_cuda(x, weight, out)
+    rows, cols = x.shape
+    check(lib().svlm_rmsnorm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), rows, cols, eps, _stream()), "svlm_rmsnorm")
+
+
+# ------------------------------------------------------------------------------------------------
+# torch custom ops (`torch.ops.svlm.*`): the thin custom-op layer the patched HF modules call.
+# ------------------------------------------------------------------------------------------------
+_ops_registered = False
+
+
+def register_torch_ops():
+    global _ops_registered
+    if _ops_registered:
+        return
+    _ops_registered = True
+    L = torch.library.Library("svlm", "DEF")
+    L.define("kv_compact_rope(Tensor(a!) arena, int src_buffer, int[] runs, Tensor pos, Tensor cos_table, Tensor sin_table, int[] section) -> ()")
+    L.define("mrope_positions(Tensor ids, Tensor grids, Tensor(a!) pos, Tensor(b!) next_pos, Tensor(c!) status, int spatial_merge, int t_step, int video_token_id) -> ()")
+    L.define("qkv_rope_append(Tensor(a!) arena, int buffer, int layer, Tensor q, Tensor k, Tensor v, Tensor(b!) q_out, int start, Tensor pos, Tensor cos_table, Tensor sin_table, int[] section) -> ()")
+    L.define("attn_causal(Tensor arena, int buffer, int layer, Tensor q, int kv_len, float scale, int num_splits) -> Tensor")
+    L.define("vit_attn(Tensor(a!) qkv, Tensor cos, Tensor sin, Tensor cu_seqlens, float scale) -> Tensor")
+    L.define("gemm_bf16(Tensor a, Tensor w, Tensor? bias, int act, Tensor? out_rows) -> Tensor")
+    L.define("rmsnorm(Tensor x, Tensor weight, float eps) -> Tensor")
+
+    def _kv_compact_rope(arena, src_buffer, runs, pos, cos_table, sin_table, section):
+        kv_compact_rope(ArenaView(arena), src_buffer, [tuple(runs[i:i + 3]) for i in range(0, len(runs), 3)], pos, cos_table,
+                        sin_table, section)
+
+    def _mrope_positions(ids, grids, pos, next_pos, status, spatial_merge, t_step, video_token_id):
+        mrope_positions(ids.reshape(-1), ids.numel(), grids, grids.shape[0], pos, next_pos, status, spatial_merge, t_step,
+                        video_token_id)
+
+    def _qkv_rope_append(arena, buffer, layer, q, k, v, q_out, start, pos, cos_table, sin_table, section):
+        qkv_rope_append(ArenaView(arena), buffer, layer, q, k, v, q.shape[0], q_out.shape[1], q_out, start, pos, cos_table,
+                        sin_table, section)
+
+    def _attn_causal(arena, buffer, layer, q, kv_len, scale, num_splits):
+        out = torch.empty_like(q)
+        ws = None
+        if num_splits > 1:
+            ws = torch.empty(attn_workspace_bytes(q.shape[0], q.shape[1], q.shape[2], num_splits) // 4, dtype=torch.float32,
+                             device=q.device)
+        attn_causal(ArenaView(arena), buffer, layer, q, out, q.shape[0], q.shape[1], kv_len, scale, num_splits, ws)
+        return out
+
+    def _vit_attn(qkv, cos, sin, cu_seqlens, scale):
+        n, _, h, d = qkv.shape
+        vit_rope(qkv, cos, sin, n, h, d)
+        out = torch.empty(n, h, d, dtype=qkv.dtype, device=qkv.device)
+        vit_attn(qkv, cu_seqlens, out, n, h, d, scale)
+        return out
+
+    def _gemm(a, w, bias, act, out_rows):
+        out = torch.empty(a.shape[0], w.shape[0], dtype=a.dtype, device=a.device)
+        gemm_bf16(a, w, bias, out, act, out_rows)
+        return out
+
+    def _rmsnorm(x, weight, eps):
+        out = torch.empty_like(x)
+        rmsnorm(x, weight, out, eps)
+        return out
+
+    for name, fn in [("kv_compact_rope", _kv_compact_rope), ("mrope_positions", _mrope_positions),
+                     ("qkv_rope_append", _qkv_rope_append), ("attn_causal", _attn_causal), ("vit_attn", _vit_attn),
+                     ("gemm_bf16", _gemm), ("rmsnorm", _rmsnorm)]:
+        L.impl(name, fn, "CUDA")
+    register_torch_ops._lib = L     # keep the Library object alive

@@ -1,0 +1,457 @@
+// Flash-attention forward for sm_100a, hand-written on tcgen05 / TMEM / TMA.
+//
+// One kernel serves the three attention shapes of the hot path:
+//   * LLM chunk prefill  (Tq ~ 276, causal bottom-right, GQA: the G query heads that share a KV head are
+//     packed into the 128-row UMMA M tile as (token, head-in-group) rows)       -- svlm_attn_causal
+//   * LLM decode         (Tq = 1, same kernel, KV range split across CTAs + merge kernel, HBM bound)
+//   * ViT windowed / full attention (non-causal, packed sequences given by cu_seqlens, head_dim 80 zero-padded
+//     to 128 by TMA out-of-bounds fill)                                          -- svlm_vit_attn
+//
+// CTA = 192 threads, 1 CTA / SM:
+//   warp 0     TMA producer: Q tile once, then a 3-stage ring of K and V tiles (128 keys x 128 dims, two
+//              64-column panels each, 128B swizzle)
+//   warp 1     UMMA issuer (one lane): S(j+1) = Q K_{j+1}^T is issued before O += P_j V_j, so the tensor pipe
+//              works on the next score tile while the softmax warps process the current one
+//   warps 2-5  online softmax, one thread per query row: tcgen05.ld the fp32 score row from TMEM, exp2 with the
+//              running (lazily updated) row max, write P as bf16 back into the same TMEM columns (A operand of
+//              the PV UMMA), rescale O in TMEM only when the max moved by more than 2^8; epilogue O / l.
+// TMEM: S0 [0,128) | S1 [128,256) | O [256,384) columns, fp32, 128 lanes.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace svlm {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int ATT_STAGES = 3;
+constexpr int PANEL_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int TILE_BYTES = 2 * PANEL_BYTES;     // 128 rows x 128 bf16
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_SMEM = 1024 + TILE_BYTES * (1 + 2 * ATT_STAGES) + 512;
+constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
+
+constexpr int MODE_CAUSAL = 0;
+constexpr int MODE_VARLEN = 1;
+
+struct AttnParams {
+    int Tq, Hq, G, D;          // D = true head dim (<= 128, multiple of 16)
+    int tpt;                   // tokens per M tile = 128 / G
+    int kv_len;                // causal: valid keys incl. the Tq new ones (host value)
+    const int32_t* kv_len_dev; // optional device override of kv_len
+    int num_splits;
+    const int32_t* cu_seqlens; // varlen
+    int n_seqs;
+    int kv_head_base;          // coordinate offset of this layer in the K/V tensor maps (layer * Hkv)
+    uint16_t* out;             // bf16 [Tq][Hq][D]
+    float* part_o;             // fp32 [splits][Tq][Hq][D]   (num_splits > 1)
+    float2* part_ml;           // (m, l) [splits][Tq][Hq]
+    float scale_log2;          // softmax scale * log2(e)
+};
+
+struct AttnBars {
+    uint64_t q_full;
+    uint64_t k_full[ATT_STAGES], k_empty[ATT_STAGES];
+    uint64_t v_full[ATT_STAGES], v_empty[ATT_STAGES];
+    uint64_t s_full[2], p_full[2];
+    uint64_t o_done[2];   // PV(j) completion alternates between the two (see the wait in the softmax warps)
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int find_seq(const int32_t* cu, int n_seqs, int tok) {
+    int lo = 0, hi = n_seqs - 1;           // largest s with cu[s] <= tok
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(cu + mid) <= tok) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;
+    uint8_t* sV = sK + ATT_STAGES * TILE_BYTES;
+    AttnBars* bars = reinterpret_cast<AttnBars*>(sV + ATT_STAGES * TILE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
+            mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->p_full[b], 128); }
+        mbar_init(&bars->o_done[0], 1); mbar_init(&bars->o_done[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    // ---- work assignment (identical arithmetic in every warp) -------------------------------------
+    const int tok0 = m_tile * p.tpt;
+    const int tokL = min(tok0 + p.tpt, p.Tq) - 1;
+    int kv_len = 0, off = 0, kv_lo_min, kv_hi_max;
+    if (MODE == MODE_CAUSAL) {
+        kv_len = p.kv_len_dev ? __ldg(p.kv_len_dev) : p.kv_len;
+        off = kv_len - p.Tq;
+        kv_lo_min = 0;
+        kv_hi_max = min(kv_len, off + tokL + 1);
+    } else {
+        kv_lo_min = __ldg(p.cu_seqlens + find_seq(p.cu_seqlens, p.n_seqs, tok0));
+        kv_hi_max = __ldg(p.cu_seqlens + find_seq(p.cu_seqlens, p.n_seqs, tokL) + 1);
+    }
+    const int t_begin = kv_lo_min / BN;
+    const int t_end = (max(kv_hi_max, 0) + BN - 1) / BN;
+    const int n_total = max(t_end - t_begin, 0);
+    const int tps = (n_total + p.num_splits - 1) / p.num_splits;
+    const int my_begin = t_begin + split * tps;
+    const int n_tiles = max(min(t_end, my_begin + tps) - my_begin, 0);
+    const int kv_coord = p.kv_head_base + head;
+
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, 128, 0, 1);
+    const int ksteps = p.D / 16;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t q_bytes = 2u * 128u * (uint32_t)(p.G * p.tpt);
+            mbar_arrive_expect_tx(&bars->q_full, q_bytes);
+            tma_load_4d(sQ, &tmQ, &bars->q_full, 0, 0, tok0, head);
+            tma_load_4d(sQ + PANEL_BYTES, &tmQ, &bars->q_full, 64, 0, tok0, head);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % ATT_STAGES;
+                const uint32_t ph = (j / ATT_STAGES) & 1;
+                const int row = (my_begin + j) * BN;
+                mbar_wait(&bars->k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bars->k_full[s], TILE_BYTES);
+                tma_load_3d(sK + s * TILE_BYTES, &tmK, &bars->k_full[s], 0, row, kv_coord);
+                tma_load_3d(sK + s * TILE_BYTES + PANEL_BYTES, &tmK, &bars->k_full[s], 64, row, kv_coord);
+                mbar_wait(&bars->v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bars->v_full[s], TILE_BYTES);
+                tma_load_3d(sV + s * TILE_BYTES, &tmV, &bars->v_full[s], 0, row, kv_coord);
+                tma_load_3d(sV + s * TILE_BYTES + PANEL_BYTES, &tmV, &bars->v_full[s], 64, row, kv_coord);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== UMMA issuer ===========================
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t q_addr = smem_u32(sQ);
+            auto issue_qk = [&](int stage, int buf) {
+                const uint32_t k_addr = smem_u32(sK + stage * TILE_BYTES);
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint32_t o = (uint32_t)(kk >> 2) * PANEL_BYTES + (uint32_t)(kk & 3) * 32u;
+                    umma_ss(tmem + buf * 128, umma_desc_sw128(q_addr + o, 16, 1024), umma_desc_sw128(k_addr + o, 16, 1024), IDESC_QK,
+                            kk > 0 ? 1u : 0u);
+                }
+            };
+            auto issue_pv = [&](int stage, int buf, bool acc) {
+                const uint32_t v_addr = smem_u32(sV + stage * TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {
+                    // B = V tile, MN-major: 16 keys (rows of 128 B) per step, two 64-column panels PANEL_BYTES apart
+                    umma_ts(tmem + 256, tmem + buf * 128 + kk * 8, umma_desc_sw128(v_addr + kk * 2048, PANEL_BYTES, 1024), IDESC_PV,
+                            (acc || kk > 0) ? 1u : 0u);
+                }
+            };
+            mbar_wait(&bars->q_full, 0);
+            mbar_wait(&bars->k_full[0], 0);
+            tc_fence_after();
+            issue_qk(0, 0);
+            umma_commit(&bars->k_empty[0]);
+            umma_commit(&bars->s_full[0]);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) {
+                    const int s1 = (j + 1) % ATT_STAGES;
+                    mbar_wait(&bars->k_full[s1], ((j + 1) / ATT_STAGES) & 1);
+                    tc_fence_after();
+                    issue_qk(s1, (j + 1) & 1);
+                    umma_commit(&bars->k_empty[s1]);
+                    umma_commit(&bars->s_full[(j + 1) & 1]);
+                }
+                const int s = j % ATT_STAGES;
+                mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);
+                mbar_wait(&bars->v_full[s], (j / ATT_STAGES) & 1);
+                tc_fence_after();
+                issue_pv(s, j & 1, j > 0);
+                umma_commit(&bars->v_empty[s]);
+                umma_commit(&bars->o_done[j & 1]);
+            }
+        }
+    } else {
+        // =========================== softmax + epilogue ===========================
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const int tok = tok0 + row / p.G;
+        const int g = row % p.G;
+        const bool valid = (row < p.G * p.tpt) && (tok < p.Tq);
+        int lo = 0, hi = 0;
+        if (valid) {
+            if (MODE == MODE_CAUSAL) {
+                hi = min(kv_len, off + tok + 1);
+            } else {
+                const int s = find_seq(p.cu_seqlens, p.n_seqs, tok);
+                lo = __ldg(p.cu_seqlens + s);
+                hi = __ldg(p.cu_seqlens + s + 1);
+            }
+        }
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int b = j & 1;
+            const int kv0 = (my_begin + j) * BN;
+            mbar_wait(&bars->s_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sr[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + b * 128 + c * 32, sr[c]);
+            tmem_wait_ld();
+            const bool need_mask = (kv0 < lo) || (kv0 + BN > hi);
+            float mt = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(sr[c][i]) * p.scale_log2;
+                    if (need_mask) {
+                        const int kv = kv0 + c * 32 + i;
+                        if (kv < lo || kv >= hi) x = -INFINITY;
+                    }
+                    sr[c][i] = __float_as_uint(x);
+                    mt = fmaxf(mt, x);
+                }
+            }
+            const bool upd = mt > m_run + RESCALE_THRESHOLD;      // also true for the first finite tile (m_run = -inf)
+            const float m_new = upd ? mt : m_run;
+            const float alpha = upd ? exp2f(m_run - m_new) : 1.0f; // m_run = -inf -> 0
+            if (__any_sync(0xffffffffu, upd && j > 0)) {
+                // rescale the running O row; PV(j-1) must have landed first.  s_full(j) observed => PV(j-3) and
+                // everything older completed, so barrier (j-1)&1 is in one of exactly two states and the parity
+                // test is unambiguous even though earlier phases were never waited on.
+                mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t orow[32];
+                    tmem_ld32(tmem + lane_addr + 256 + c * 32, orow);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+                    tmem_st32(tmem + lane_addr + 256 + c * 32, orow);
+                }
+            }
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = exp2f(__uint_as_float(sr[c][2 * i]) - m_use);
+                    const float p1 = exp2f(__uint_as_float(sr[c][2 * i + 1]) - m_use);
+                    lsum += p0 + p1;
+                    pk[i] = pack_bf16(p0, p1);
+                }
+                tmem_st16(tmem + lane_addr + b * 128 + c * 16, pk);
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars->p_full[b]);
+        }
+
+        // ---- epilogue ----
+        if (n_tiles > 0) {
+            mbar_wait(&bars->o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+            tc_fence_after();
+        }
+        const int hq = head * p.G + g;
+        const float inv = (p.num_splits == 1) ? (l_run > 0.f ? 1.0f / l_run : 0.f) : 1.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t orow[32];
+            if (n_tiles > 0) {
+                tmem_ld32(tmem + lane_addr + 256 + c * 32, orow);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) orow[i] = 0u;
+            }
+            if (valid) {
+                if (p.num_splits == 1) {
+                    uint16_t* dst = p.out + ((int64_t)tok * p.Hq + hq) * p.D + c * 32;
+#pragma unroll
+                    for (int v8 = 0; v8 < 4; ++v8) {
+                        if (c * 32 + v8 * 8 < p.D) {
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(orow[v8 * 8 + 0]) * inv, __uint_as_float(orow[v8 * 8 + 1]) * inv);
+                            o.y = pack_bf16(__uint_as_float(orow[v8 * 8 + 2]) * inv, __uint_as_float(orow[v8 * 8 + 3]) * inv);
+                            o.z = pack_bf16(__uint_as_float(orow[v8 * 8 + 4]) * inv, __uint_as_float(orow[v8 * 8 + 5]) * inv);
+                            o.w = pack_bf16(__uint_as_float(orow[v8 * 8 + 6]) * inv, __uint_as_float(orow[v8 * 8 + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + v8 * 8) = o;
+                        }
+                    }
+                } else {
+                    float* dst = p.part_o + (((int64_t)split * p.Tq + tok) * p.Hq + hq) * p.D + c * 32;
+#pragma unroll
+                    for (int v4 = 0; v4 < 8; ++v4) {
+                        if (c * 32 + v4 * 4 < p.D)
+                            *reinterpret_cast<uint4*>(dst + v4 * 4) = make_uint4(orow[v4 * 4], orow[v4 * 4 + 1], orow[v4 * 4 + 2], orow[v4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        if (valid && p.num_splits > 1) p.part_ml[((int64_t)split * p.Tq + tok) * p.Hq + hq] = make_float2(m_run, l_run);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// Merge of the split-KV partials: out = sum_s 2^(m_s - M) O_s / sum_s 2^(m_s - M) l_s.
+// grid = Tq * Hq, block = 128 (one thread per output column).
+__global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                                            uint16_t* __restrict__ out, int rows, int D, int num_splits) {
+    const int r = blockIdx.x, d = threadIdx.x;
+    float M = -INFINITY;
+    for (int s = 0; s < num_splits; ++s) M = fmaxf(M, part_ml[(int64_t)s * rows + r].x);
+    float L = 0.f, acc = 0.f;
+    for (int s = 0; s < num_splits; ++s) {
+        const float2 ml = part_ml[(int64_t)s * rows + r];
+        const float w = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - M);
+        L += w * ml.y;
+        if (d < D && w != 0.f) acc += w * part_o[((int64_t)s * rows + r) * D + d];
+    }
+    if (d < D) out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
+}
+
+static int launch_attn(int mode, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                       cudaStream_t st) {
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[mode]) {
+        cudaError_t e = mode == MODE_CAUSAL
+                            ? cudaFuncSetAttribute(attn_fwd_kernel<MODE_CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)
+                            : cudaFuncSetAttribute(attn_fwd_kernel<MODE_VARLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_fwd_kernel, %d B smem) failed: %s", ATT_SMEM, cudaGetErrorString(e));
+            return SVLM_ECUDA;
+        }
+        attr_done[mode] = true;
+    }
+    if (mode == MODE_CAUSAL)
+        attn_fwd_kernel<MODE_CAUSAL><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+    else
+        attn_fwd_kernel<MODE_VARLEN><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+    return launch_status("attn_fwd_kernel");
+}
+
+}  // namespace svlm
+
+using namespace svlm;
+
+extern "C" size_t svlm_attn_workspace_bytes(int n_q_tokens, int q_heads, int head_dim, int num_splits) {
+    if (num_splits <= 1) return 0;
+    const size_t rows = (size_t)num_splits * n_q_tokens * q_heads;
+    return rows * head_dim * sizeof(float) + rows * sizeof(float2);
+}
+
+extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int n_q_tokens, int q_heads,
+                                int kv_len, const int32_t* kv_len_dev, int num_splits, void* workspace, size_t workspace_bytes,
+                                float scale, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    if ((rc = validate_arena(arena))) return rc;
+    SVLM_REQUIRE(buffer == 0 || buffer == 1, "buffer must be 0 or 1");
+    SVLM_REQUIRE(layer >= 0 && layer < arena->layers, "layer %d out of range", layer);
+    SVLM_REQUIRE(q && out, "NULL tensor argument");
+    SVLM_REQUIRE(n_q_tokens > 0 && q_heads > 0 && q_heads % arena->kv_heads == 0, "bad n_q_tokens / q_heads");
+    SVLM_REQUIRE(kv_len >= n_q_tokens && kv_len <= arena->capacity, "kv_len %d must be in [Tq=%d, capacity=%d]", kv_len, n_q_tokens,
+                 arena->capacity);
+    SVLM_REQUIRE(num_splits >= 1 && num_splits <= 256, "num_splits %d out of range", num_splits);
+    SVLM_REQUIRE((((uintptr_t)q | (uintptr_t)out) & 15) == 0, "q/out must be 16-byte aligned");
+    const int D = arena->head_dim, H = arena->kv_heads, G = q_heads / H;
+    SVLM_REQUIRE(G <= 128, "group size %d too large", G);
+    const size_t need = svlm_attn_workspace_bytes(n_q_tokens, q_heads, D, num_splits);
+    SVLM_REQUIRE(num_splits == 1 || (workspace != nullptr && workspace_bytes >= need), "workspace too small: need %zu bytes", need);
+
+    ArenaDims ad{arena->layers, H, D, arena->capacity};
+    const uint16_t* base = (const uint16_t*)arena->base;
+    const int tpt = BM / G;
+    CUtensorMap tq, tk, tv;
+    {
+        uint64_t dims[4] = {(uint64_t)D, (uint64_t)G, (uint64_t)n_q_tokens, (uint64_t)H};
+        uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)q_heads * D * 2, (uint64_t)G * D * 2};
+        uint32_t box[4] = {64, (uint32_t)G, (uint32_t)tpt, 1};
+        if ((rc = make_tensor_map_bf16(&tq, q, 4, dims, str, box, 1))) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)D, (uint64_t)ad.cap, (uint64_t)ad.L * H};
+        uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)ad.cap * D * 2};
+        uint32_t box[3] = {64, BN, 1};
+        if ((rc = make_tensor_map_bf16(&tk, base + ad.offset(buffer, SVLM_PLANE_K_ROT, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&tv, base + ad.offset(buffer, SVLM_PLANE_V, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+    }
+    AttnParams p{};
+    p.Tq = n_q_tokens; p.Hq = q_heads; p.G = G; p.D = D; p.tpt = tpt;
+    p.kv_len = kv_len; p.kv_len_dev = kv_len_dev; p.num_splits = num_splits;
+    p.kv_head_base = layer * H;
+    p.out = (uint16_t*)out;
+    const size_t rows = (size_t)num_splits * n_q_tokens * q_heads;
+    p.part_o = (float*)workspace;
+    p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + rows * D) : nullptr;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    dim3 grid((n_q_tokens + tpt - 1) / tpt, H, num_splits);
+    if ((rc = launch_attn(MODE_CAUSAL, tq, tk, tv, p, grid, (cudaStream_t)stream))) return rc;
+    if (num_splits > 1) {
+        attn_combine_kernel<<<n_q_tokens * q_heads, 128, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, n_q_tokens * q_heads, D, num_splits);
+        return launch_status("attn_combine_kernel");
+    }
+    return SVLM_OK;
+}
+
+extern "C" int svlm_vit_attn(const void* qkv, const int32_t* cu_seqlens, int n_seqs, void* out, int n_tokens, int heads, int head_dim,
+                             float scale, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(qkv && cu_seqlens && out, "NULL tensor argument");
+    SVLM_REQUIRE(n_tokens > 0 && heads > 0 && n_seqs > 0, "bad n_tokens / heads / n_seqs");
+    SVLM_REQUIRE(head_dim % 16 == 0 && head_dim <= 128 && head_dim >= 16, "head_dim %d must be a multiple of 16 in [16,128]", head_dim);
+    SVLM_REQUIRE((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "qkv/out must be 16-byte aligned");
+    const int D = head_dim;
+    const uint16_t* base = (const uint16_t*)qkv;
+    const uint64_t tok_stride = (uint64_t)3 * heads * D * 2;
+    CUtensorMap tq, tk, tv;
+    {
+        uint64_t dims[4] = {(uint64_t)D, 1, (uint64_t)n_tokens, (uint64_t)heads};
+        uint64_t str[3] = {(uint64_t)D * 2, tok_stride, (uint64_t)D * 2};
+        uint32_t box[4] = {64, 1, BM, 1};
+        if ((rc = make_tensor_map_bf16(&tq, base, 4, dims, str, box, 1))) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)D, (uint64_t)n_tokens, (uint64_t)heads};
+        uint64_t str[2] = {tok_stride, (uint64_t)D * 2};
+        uint32_t box[3] = {64, BN, 1};
+        if ((rc = make_tensor_map_bf16(&tk, base + (size_t)heads * D, 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&tv, base + (size_t)2 * heads * D, 3, dims, str, box, 1))) return rc;
+    }
+    AttnParams p{};
+    p.Tq = n_tokens; p.Hq = heads; p.G = 1; p.D = D; p.tpt = BM;
+    p.num_splits = 1; p.cu_seqlens = cu_seqlens; p.n_seqs = n_seqs; p.kv_head_base = 0;
+    p.out = (uint16_t*)out;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    dim3 grid((n_tokens + BM - 1) / BM, heads, 1);
+    return launch_attn(MODE_VARLEN, tq, tk, tv, p, grid, (cudaStream_t)stream);
+}

@@ -1,0 +1,294 @@
+"""GPU parity: every CUDA kernel, through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bit-exact for integer / byte / bf16-elementwise work (compaction, positions, mRoPE, ViT RoPE);
+stated bf16 tolerances for the softmax / GEMM rows.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as o_attn
+from oracle import positions as o_pos
+from oracle import vit as o_vit
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+SECTION = (16, 24, 24)
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from streaming_vlm_b200 import _abi
+    _abi.build()
+    assert _abi.lib().svlm_version() == 1
+    return _abi
+
+
+@pytest.fixture(scope="module")
+def tables():
+    cos, sin = o_pos.rotary_table(4096, o_pos.default_inv_freq(128, 1e6))
+    return cos.contiguous(), sin.contiguous()
+
+
+def bits(t):
+    return t.contiguous().view(torch.int16)
+
+
+def make_arena(abi, L, H, cap, seed=0, fill=True):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.zeros(2, 3, L, H, cap, 128, dtype=torch.bfloat16)
+    if fill:
+        a[0] = (torch.randn(3, L, H, cap, 128, generator=g) * 0.5).to(torch.bfloat16)
+    dev = a.to(DEV)
+    return a, dev, abi.ArenaView(dev)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("m,n,k,act,perm", [(256, 5120, 5120, 1, False), (256, 3584, 5120, 0, True), (100, 72, 200, 1, True),
+                                            (128, 128, 64, 0, False), (1024, 3840, 1280, 0, False), (37, 512, 1280, 1, False)])
+def test_gemm_bf16(abi, m, n, k, act, perm):
+    g = torch.Generator().manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    b = (torch.randn(n, generator=g) * 0.1).to(torch.bfloat16)
+    ref = torch.nn.functional.linear(a.float(), w.float(), b.float()).to(torch.bfloat16)
+    if act:
+        ref = torch.nn.functional.gelu(ref.float()).to(torch.bfloat16)
+    rows = None
+    if perm:
+        p = torch.randperm(m, generator=g)
+        rows = p.to(torch.int32).to(DEV)
+        ref_p = torch.empty_like(ref)
+        ref_p[p] = ref
+        ref = ref_p
+    out = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_bf16(a.to(DEV), w.to(DEV), b.to(DEV), out, act, rows)
+    torch.cuda.synchronize()
+    # fp32-accumulated bf16 GEMM: one bf16 ulp of the result magnitude
+    torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=1.6e-2, atol=1.6e-2)
+
+
+def test_rmsnorm(abi):
+    g = torch.Generator().manual_seed(3)
+    for rows, cols in [(1024, 1280), (276, 3584), (1, 512)]:
+        x = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
+        w = (1 + 0.1 * torch.randn(cols, generator=g)).to(torch.bfloat16)
+        out = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+        abi.rmsnorm(x.to(DEV), w.to(DEV), out, 1e-6)
+        ref = o_vit.rmsnorm(x, w, 1e-6)
+        # rsqrtf vs CPU rsqrt may differ in the last fp32 bit -> at most one bf16 ulp
+        torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=8e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ positions
+def test_mrope_positions_bit_exact(abi, golden_dir):
+    z = np.load(os.path.join(golden_dir, "rope_index.npz"))
+    names = sorted({k.split("__")[0] for k in z.files})
+    for nme in names:
+        ids = torch.from_numpy(z[nme + "__ids"]).to(DEV)
+        grid = z[nme + "__grid"].tolist()
+        n = ids.numel()
+        grids = torch.tensor([grid] * 64, dtype=torch.int32, device=DEV)
+        pos = torch.full((3, n + 5), -7, dtype=torch.int32, device=DEV)
+        nxt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        status = torch.zeros(1, dtype=torch.int32, device=DEV)
+        abi.mrope_positions(ids, n, grids, 64, pos, nxt, status)
+        ref = z[nme + "__pos"][:, 0, :]
+        assert status.item() == 0, nme
+        assert np.array_equal(pos[:, :n].cpu().numpy().astype(np.float32), ref), nme
+        assert nxt.item() == int(ref.max()) + 1
+        assert (pos[:, n:] == -7).all()
+
+
+def test_mrope_positions_long_and_edge(abi):
+    """64k-token sequence (scan across all 1024 threads), empty input, grid mismatch flag."""
+    from streaming_vlm_b200 import synthetic
+    ids = []
+    for i in range(220):
+        ids += synthetic.round_prompt(i, 256, 24, 8, 0) + [5000 + i] * 9 + [151645]
+    ids = ids[:65000]
+    while ids[-1] == 151656:
+        ids.pop()
+    ref, _ = o_pos.get_rope_index(ids, [[1, 32, 32]] * 300)
+    t = torch.tensor(ids, dtype=torch.int64, device=DEV)
+    grids = torch.tensor([[1, 32, 32]] * 300, dtype=torch.int32, device=DEV)
+    pos = torch.zeros(3, len(ids), dtype=torch.int32, device=DEV)
+    nxt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    abi.mrope_positions(t, len(ids), grids, 300, pos, nxt, status)
+    assert status.item() == 0
+    assert np.array_equal(pos.cpu().numpy().astype(np.float32), ref[:, 0].numpy())
+    abi.mrope_positions(t, 0, grids, 300, pos, nxt, status)
+    assert nxt.item() == 0
+    bad = torch.tensor([[1, 30, 32]] * 300, dtype=torch.int32, device=DEV)
+    abi.mrope_positions(t, len(ids), bad, 300, pos, nxt, status)
+    assert status.item() & 1
+
+
+# ------------------------------------------------------------------------------------------------ compaction + RoPE
+def _oracle_compact(arena_cpu, gather, pos_f32, tables):
+    """new K_raw / V = gather; K_rot = reference mRoPE of the gathered raw keys."""
+    idx = torch.tensor(gather, dtype=torch.long)
+    k_raw = arena_cpu[0, 0].index_select(2, idx)        # [L,H,n,D]
+    v = arena_cpu[0, 2].index_select(2, idx)
+    cos, sin = o_pos.rotary_cos_sin(pos_f32, o_pos.default_inv_freq(128, 1e6))
+    L, H, n, D = k_raw.shape
+    _, k_rot = o_pos.apply_mrope(k_raw.reshape(1, L * H, n, D)[:, :1, :1], k_raw.reshape(1, L * H, n, D), cos, sin, SECTION)
+    return k_raw, k_rot.reshape(L, H, n, D), v
+
+
+@pytest.mark.parametrize("stream_idx,round_idx", [(0, -1), (0, 16), (1, -1), (2, -1), (3, -1), (4, -1)])
+def test_kv_compact_rope_bit_exact(abi, tables, golden_dir, stream_idx, round_idx):
+    streams = json.load(open(os.path.join(golden_dir, "eviction_streams.json")))
+    rec = streams[stream_idx]["rounds"][round_idx]
+    runs_rle = rec["cache_runs"]                      # [(src_start, len)] from the reference itself
+    gather = [s + i for s, l in runs_rle for i in range(l)]
+    n_src = rec["before_len"]
+    cap = ((n_src + 127) // 128) * 128 + 128
+    L, H = 2, 2
+    arena_cpu, arena_dev, view = make_arena(abi, L, H, cap, seed=stream_idx)
+    runs, d = [], 0
+    for s, l in runs_rle:
+        runs.append((s, d, l))
+        d += l
+    n = len(gather)
+    # contiguous positions of the pruned sequence (any valid positions exercise the kernel; use real ones)
+    g = torch.Generator().manual_seed(5)
+    pos_i = torch.sort(torch.randint(0, 2000, (3, cap), generator=g), dim=1).values.to(torch.int32)
+    pos_dev = pos_i.to(DEV)
+    cos, sin = tables
+    abi.kv_compact_rope(view, 0, runs, pos_dev, cos.to(DEV), sin.to(DEV), SECTION)
+    torch.cuda.synchronize()
+    got = arena_dev.cpu()
+    k_raw, k_rot, v = _oracle_compact(arena_cpu, gather, pos_i[:, None, :n].float(), tables)
+    assert torch.equal(bits(got[1, 0, :, :, :n]), bits(k_raw))
+    assert torch.equal(bits(got[1, 2, :, :, :n]), bits(v))
+    assert torch.equal(bits(got[1, 1, :, :, :n]), bits(k_rot))
+    assert torch.equal(bits(got[0]), bits(arena_cpu[0])), "source buffer must be untouched"
+    assert (got[1, :, :, :, n:] == 0).all(), "rows past the retained length must not be written"
+
+
+def test_kv_compact_rope_argument_errors(abi, tables):
+    _, _, view = make_arena(abi, 1, 1, 256, fill=False)
+    pos = torch.zeros(3, 256, dtype=torch.int32, device=DEV)
+    cos, sin = (t.to(DEV) for t in tables)
+    with pytest.raises(RuntimeError, match="contiguously"):
+        abi.kv_compact_rope(view, 0, [(0, 5, 10)], pos, cos, sin, SECTION)
+    with pytest.raises(RuntimeError, match="capacity"):
+        abi.kv_compact_rope(view, 0, [(250, 0, 10)], pos, cos, sin, SECTION)
+    with pytest.raises(RuntimeError, match="SVLM_MAX_RUNS"):
+        abi.kv_compact_rope(view, 0, [(i, i, 1) for i in range(40)], pos, cos, sin, SECTION)
+    abi.kv_compact_rope(view, 0, [], pos, cos, sin, SECTION)      # empty gather is a no-op
+
+
+def test_qkv_rope_append_bit_exact(abi, tables):
+    L, H, cap, Hq, T, start = 2, 2, 512, 4, 37, 200
+    arena_cpu, arena_dev, view = make_arena(abi, L, H, cap, seed=9)
+    arena_dev[1].copy_(arena_dev[0])
+    g = torch.Generator().manual_seed(4)
+    qkv = (torch.randn(T, (Hq + 2 * H) * 128, generator=g)).to(torch.bfloat16)
+    qkv_d = qkv.to(DEV)
+    q, k, v = qkv_d[:, :Hq * 128], qkv_d[:, Hq * 128:(Hq + H) * 128], qkv_d[:, (Hq + H) * 128:]
+    pos_i = torch.sort(torch.randint(0, 3000, (3, cap), generator=g), dim=1).values.to(torch.int32)
+    cos, sin = tables
+    q_out = torch.zeros(T, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    abi.qkv_rope_append(view, 1, 1, q, k, v, T, Hq, q_out, start, pos_i.to(DEV), cos.to(DEV), sin.to(DEV), SECTION)
+    torch.cuda.synchronize()
+    pf = pos_i[:, None, start:start + T].float()
+    c, s = o_pos.rotary_cos_sin(pf, o_pos.default_inv_freq(128, 1e6))
+    q_ref, k_ref = o_pos.apply_mrope(qkv[:, :Hq * 128].view(1, T, Hq, 128).transpose(1, 2),
+                                     qkv[:, Hq * 128:(Hq + H) * 128].view(1, T, H, 128).transpose(1, 2), c, s, SECTION)
+    got = arena_dev.cpu()
+    assert torch.equal(bits(q_out.cpu()), bits(q_ref[0].transpose(0, 1)))
+    assert torch.equal(bits(got[1, 1, 1, :, start:start + T]), bits(k_ref[0]))
+    assert torch.equal(bits(got[1, 0, 1, :, start:start + T]), bits(qkv[:, Hq * 128:(Hq + H) * 128].view(T, H, 128).transpose(0, 1)))
+    assert torch.equal(bits(got[1, 2, 1, :, start:start + T]), bits(qkv[:, (Hq + H) * 128:].view(T, H, 128).transpose(0, 1)))
+    # everything else untouched
+    got[1, :, 1, :, start:start + T] = arena_cpu[0, :, 1, :, start:start + T]
+    assert torch.equal(bits(got[1]), bits(arena_cpu[0]))
+    # decode form: start and text position read from device memory
+    start_dev = torch.tensor([start + T], dtype=torch.int32, device=DEV)
+    tpos = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    q1 = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    abi.qkv_rope_append(view, 1, 0, q[:1], k[:1], v[:1], 1, Hq, q1, 0, None, cos.to(DEV), sin.to(DEV), SECTION,
+                        start_dev=start_dev, text_pos_dev=tpos)
+    pf = torch.full((3, 1, 1), 1234.0)
+    c, s = o_pos.rotary_cos_sin(pf, o_pos.default_inv_freq(128, 1e6))
+    q_ref, k_ref = o_pos.apply_mrope(qkv[:1, :Hq * 128].view(1, 1, Hq, 128).transpose(1, 2),
+                                     qkv[:1, Hq * 128:(Hq + H) * 128].view(1, 1, H, 128).transpose(1, 2), c, s, SECTION)
+    assert torch.equal(bits(q1.cpu()), bits(q_ref[0].transpose(0, 1)))
+    assert torch.equal(bits(arena_dev[1, 1, 0, :, start + T].cpu()), bits(k_ref[0, :, 0]))
+
+
+# ------------------------------------------------------------------------------------------------ attention
+ATT_TOL = dict(rtol=2e-2, atol=6e-3)   # bf16 output, bf16 P; |out| <~ 1
+
+
+def _attn_case(abi, Hq, H, Tq, S, splits, seed):
+    cap = ((S + 127) // 128) * 128 + 128
+    L = 2
+    arena_cpu, arena_dev, view = make_arena(abi, L, H, cap, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    q = torch.randn(Tq, Hq, 128, generator=g).to(torch.bfloat16)
+    out = torch.zeros(Tq, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    ws = None
+    if splits > 1:
+        ws = torch.zeros(abi.attn_workspace_bytes(Tq, Hq, 128, splits) // 4, dtype=torch.float32, device=DEV)
+    layer = 1
+    abi.attn_causal(view, 0, layer, q.to(DEV), out, Tq, Hq, S, 1.0 / math.sqrt(128), splits, ws)
+    torch.cuda.synchronize()
+    ref = o_attn.attention(q.transpose(0, 1), arena_cpu[0, 1, layer, :, :S], arena_cpu[0, 2, layer, :, :S], causal=True)
+    return out.cpu().float().reshape(Tq, -1), ref.float()
+
+
+@pytest.mark.parametrize("Hq,H,Tq,S,splits", [
+    (4, 2, 1, 128, 1), (4, 2, 1, 300, 1), (4, 2, 64, 64, 1), (4, 2, 130, 700, 1),
+    (28, 4, 276, 5619, 1), (28, 4, 276, 5619, 2), (28, 4, 1, 5343, 1), (28, 4, 1, 5343, 37), (28, 4, 1, 130, 8),
+    (40, 8, 33, 1000, 3), (4, 2, 300, 300, 1),
+])
+def test_attn_causal(abi, Hq, H, Tq, S, splits):
+    got, ref = _attn_case(abi, Hq, H, Tq, S, splits, seed=Hq + Tq + S)
+    torch.testing.assert_close(got, ref, **ATT_TOL)
+
+
+def test_attn_decode_kv_len_from_device(abi):
+    Hq, H, S = 28, 4, 4000
+    cap = 4224
+    arena_cpu, arena_dev, view = make_arena(abi, 1, H, cap, seed=1)
+    q = torch.randn(1, Hq, 128, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    out = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    splits = 16
+    ws = torch.zeros(abi.attn_workspace_bytes(1, Hq, 128, splits) // 4, dtype=torch.float32, device=DEV)
+    kv = torch.tensor([S], dtype=torch.int32, device=DEV)
+    abi.attn_causal(view, 0, 0, q.to(DEV), out, 1, Hq, cap, 1.0 / math.sqrt(128), splits, ws, kv_len_dev=kv)
+    ref = o_attn.attention(q.transpose(0, 1), arena_cpu[0, 1, 0, :, :S], arena_cpu[0, 2, 0, :, :S], causal=True)
+    torch.testing.assert_close(out.cpu().float().reshape(1, -1), ref.float(), **ATT_TOL)
+
+
+@pytest.mark.parametrize("heads,D,n,cu", [
+    (16, 80, 1024, list(range(0, 1025, 64))), (16, 80, 1024, [0, 1024]), (4, 80, 1024, list(range(0, 1025, 64))),
+    (4, 80, 300, [0, 64, 100, 228, 300]), (2, 128, 256, [0, 256]),
+])
+def test_vit_rope_and_attention(abi, heads, D, n, cu):
+    g = torch.Generator().manual_seed(n + heads)
+    qkv = torch.randn(n, 3, heads, D, generator=g).to(torch.bfloat16)
+    ang = torch.rand(n, D // 2, generator=g) * 6.0
+    emb = torch.cat((ang, ang), dim=-1)
+    cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+    qkv_d = qkv.to(DEV)
+    abi.vit_rope(qkv_d, cos.to(DEV), sin.to(DEV), n, heads, D)
+    q_ref, k_ref = o_vit.apply_rope_vision(qkv[:, 0], qkv[:, 1], cos, sin)
+    got = qkv_d.cpu()
+    assert torch.equal(bits(got[:, 0]), bits(q_ref)) and torch.equal(bits(got[:, 1]), bits(k_ref))
+    assert torch.equal(bits(got[:, 2]), bits(qkv[:, 2]))
+    out = torch.zeros(n, heads, D, dtype=torch.bfloat16, device=DEV)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    abi.vit_attn(qkv_d, cu_t, out, n, heads, D, D ** -0.5)
+    torch.cuda.synchronize()
+    ref = o_attn.varlen_attention(q_ref, k_ref, qkv[:, 2], cu)
+    torch.testing.assert_close(out.cpu().float(), ref.float(), **ATT_TOL)
