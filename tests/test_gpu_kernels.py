@@ -81,8 +81,8 @@ def test_rmsnorm(abi):
         out = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
         abi.rmsnorm(x.to(DEV), w.to(DEV), out, 1e-6)
         ref = o_vit.rmsnorm(x, w, 1e-6)
-        # rsqrtf vs CPU rsqrt may differ in the last fp32 bit -> at most one bf16 ulp
-        torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=8e-3, atol=1e-3)
+        # rsqrtf vs CPU rsqrt can differ in the last fp32 bit; two bf16 roundings follow -> up to two bf16 ulps
+        torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=1.6e-2, atol=1e-3)
 
 
 # ------------------------------------------------------------------------------------------------ positions
