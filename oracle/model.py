@@ -139,6 +139,7 @@ class Session:
         full = list(ids)                       # streaming_args.input_ids
         seq = list(ids)
         n_fwd = 0
+        step_logits = []
         while True:
             cached = self.cache.get_seq_length()
             new = seq[cached:]
@@ -149,6 +150,7 @@ class Session:
             n_fwd += 1
             if self.suppress is not None:
                 logits = logits.masked_fill(self.suppress, float("-inf"))
+            step_logits.append(logits)
             tok = int(torch.argmax(logits))
             seq.append(tok)
             if tok == IM_END or len(seq) - input_len >= self.max_new_tokens:
@@ -162,4 +164,4 @@ class Session:
         self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens)})
         self.i += 1
         return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "gather": gather,
-                "cache_len": self.cache.get_seq_length()}
+                "cache_len": self.cache.get_seq_length(), "step_logits": step_logits}

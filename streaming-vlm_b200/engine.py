@@ -1,0 +1,388 @@
+"""Per-stream session runner: evict -> ViT -> chunk prefill -> greedy decode, one stream per object.
+
+This is the B200-native counterpart of the reference's `streaming_inference` chunk loop
+(`inference/inference.py:309-517`) together with the patched forwards it drives
+(`qwen2_5/model_forward.py:30-176`, `qwen2_5/language_forward.py:143-305, 395-516`,
+`qwen2_5/vision_forward.py:6-101`) and the greedy branch of `_sample`
+(`generate/streaming_generate_qwen.py:53-110`).  Differences in execution, not in results:
+
+* the K/V cache is a fixed arena (`StreamingCache`); eviction is ONE compaction launch per chunk,
+  positions are recomputed on the device once per chunk (the reference: host Python on every forward);
+* K is rotated once when it is appended and once per eviction (the reference re-rotates the whole
+  cache in every layer of every forward);
+* GQA is resolved inside the attention kernel (no `repeat_kv` copies); decode attention is split-KV;
+* lm_head runs on the last position only (the reference computes all and samples `[:, -1]`);
+* each decode step is one CUDA-graph replay (kv length and next position live in device memory).
+
+Dense projections go through cuBLAS (`torch.nn.functional.linear`); every other op on the path is a
+kernel of `libsvlm_b200.so`.  Section timers mirror the reference's PKV / GEN (`inference.py:312-329,
+422-452`).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _abi
+from .config import Geometry
+from .inference.generate.streaming_cache import StreamingCache
+from .inference.inference import (DEFAULT_TEXT_ROUND, DEFAULT_TEXT_SINK, DEFAULT_TEXT_SLIDING_WINDOW, DEFAULT_WINDOW_SIZE,
+                                  MAX_TOKEN_PER_DURATION, plan_past_kv)
+from .utils.get_qwen_range import TOKEN_IDS
+
+IM_END = TOKEN_IDS["<|im_end|>"]
+LF = TOKEN_IDS["\n"]
+VIDEO_PAD = TOKEN_IDS["<|video_pad|>"]
+
+
+def _window_index(grid, window_size, merge, patch):
+    """HF `get_window_index` for one (t, h, w) grid -> (order of merge units, cu_seqlens in ViT tokens)."""
+    t, h, w = grid
+    ws = window_size // merge // patch
+    gh, gw = h // merge, w // merge
+    idx = np.arange(t * gh * gw).reshape(t, gh, gw)
+    ph, pw = ws - gh % ws, ws - gw % ws
+    nh, nw = (gh + ph) // ws, (gw + pw) // ws
+    pad = np.full((t, gh + ph, gw + pw), -100, dtype=np.int64)
+    pad[:, :gh, :gw] = idx
+    pad = pad.reshape(t, nh, ws, nw, ws).transpose(0, 1, 3, 2, 4).reshape(t, nh * nw, ws, ws)
+    lens = (pad != -100).sum(axis=(2, 3)).reshape(-1)
+    flat = pad.reshape(-1)
+    order = flat[flat != -100]
+    cu = np.concatenate([[0], np.cumsum(lens) * merge * merge])
+    cu = cu[np.concatenate([[True], np.diff(cu) != 0])]           # unique_consecutive (vision_forward.py:71)
+    return order, cu.astype(np.int32)
+
+
+class _VitPlan:
+    """Everything about one (t, h, w) grid that does not depend on pixel values (cached per grid)."""
+
+    def __init__(self, grid, geo: Geometry, device):
+        t, h, w = grid
+        m = geo.spatial_merge_size
+        unit = m * m
+        self.n = t * h * w
+        order, cu_win = _window_index(grid, geo.window_size, m, geo.patch_size)
+        hd = geo.vit_hidden // geo.vit_heads
+        dim = hd // 2
+        inv = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float) / dim))
+        hp = torch.arange(h)[:, None].expand(-1, w).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+        wp = torch.arange(w)[None, :].expand(h, -1).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+        pid = torch.stack([hp, wp], dim=-1).repeat(t, 1)
+        table = torch.outer(torch.arange(max(h, w), dtype=torch.float), inv)
+        emb = table[pid].flatten(1)
+        order_t = torch.from_numpy(order)
+        emb = emb.reshape(self.n // unit, unit, -1)[order_t].reshape(self.n, -1)
+        emb = torch.cat((emb, emb), dim=-1)
+        self.cos = emb.cos().contiguous().to(device)
+        self.sin = emb.sin().contiguous().to(device)
+        self.order = order_t.to(device)
+        self.out_rows = order_t.to(torch.int32).to(device)       # merged row m lands at row order[m] (argsort un-permute)
+        self.cu_window = torch.from_numpy(cu_win).to(device)
+        self.cu_full = torch.tensor([i * h * w for i in range(t + 1)], dtype=torch.int32, device=device)
+
+
+class StreamingEngine:
+    def __init__(self, weights: dict, geo: Geometry, capacity: int = 8192, device="cuda", window_size=DEFAULT_WINDOW_SIZE,
+                 text_round=DEFAULT_TEXT_ROUND, text_sink=DEFAULT_TEXT_SINK, text_sliding_window=DEFAULT_TEXT_SLIDING_WINDOW,
+                 max_new_tokens=MAX_TOKEN_PER_DURATION, suppress=None, assistant_start_bias=3, assistant_end_bias=2,
+                 use_graph=True, decode_splits=None, prefill_splits=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("StreamingEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        _abi.lib()
+        self.geo, self.device = geo, torch.device(device)
+        self.window_size, self.text_round = window_size, text_round
+        self.text_sink, self.text_sliding_window = text_sink, text_sliding_window
+        self.max_new_tokens = max_new_tokens
+        self.asb, self.aeb = assistant_start_bias, assistant_end_bias
+        self.use_graph = use_graph
+        self.suppress = None if suppress is None else suppress.to(self.device)
+        self.cache = StreamingCache(geo, capacity, self.device)
+        self.scale = 1.0 / math.sqrt(geo.head_dim)
+        self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 148 // geo.num_kv_heads))
+        self.prefill_splits = prefill_splits
+        self._prepare_weights(weights)
+        g = geo
+        dev = self.device
+        self.ws = torch.zeros(max(_abi.attn_workspace_bytes(1, g.num_heads, g.head_dim, self.decode_splits),
+                                  _abi.attn_workspace_bytes(512, g.num_heads, g.head_dim, 4)) // 4 + 16, dtype=torch.float32, device=dev)
+        self.kv_len_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.kv_after_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.tok_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.tok_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._graphs = {}
+        self._vit_plans = {}
+        # session state (reference: inference.py:297-303)
+        self.prev_ids = None
+        self.history, self.clips, self.pixels, self.grids = [], [], [], []
+        self.i = 0
+        self.timing = []
+        self.launches = 0
+
+    # ------------------------------------------------------------------ weights
+    def _prepare_weights(self, w):
+        g = self.geo
+        dev = self.device
+        mv = lambda t: t.to(dev).contiguous()
+        v = "model.visual."
+        pe = w.pop(v + "patch_embed.proj.weight")
+        self.w_patch = mv(pe.reshape(pe.shape[0], -1))
+        self.vit = []
+        for li in range(g.vit_depth):
+            b = f"{v}blocks.{li}."
+            self.vit.append(dict(
+                n1=mv(w.pop(b + "norm1.weight")), n2=mv(w.pop(b + "norm2.weight")),
+                wqkv=mv(w.pop(b + "attn.qkv.weight")), bqkv=mv(w.pop(b + "attn.qkv.bias")),
+                wproj=mv(w.pop(b + "attn.proj.weight")), bproj=mv(w.pop(b + "attn.proj.bias")),
+                wgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.weight"), w.pop(b + "mlp.up_proj.weight")], 0)),
+                bgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.bias"), w.pop(b + "mlp.up_proj.bias")], 0)),
+                wd=mv(w.pop(b + "mlp.down_proj.weight")), bd=mv(w.pop(b + "mlp.down_proj.bias"))))
+        self.merger = dict(ln=mv(w.pop(v + "merger.ln_q.weight")), w0=mv(w.pop(v + "merger.mlp.0.weight")),
+                           b0=mv(w.pop(v + "merger.mlp.0.bias")), w2=mv(w.pop(v + "merger.mlp.2.weight")),
+                           b2=mv(w.pop(v + "merger.mlp.2.bias")))
+        lm = "model.language_model."
+        self.embed = mv(w.pop(lm + "embed_tokens.weight"))
+        self.layers = []
+        for li in range(g.num_layers):
+            b = f"{lm}layers.{li}."
+            a = b + "self_attn."
+            self.layers.append(dict(
+                ln1=mv(w.pop(b + "input_layernorm.weight")), ln2=mv(w.pop(b + "post_attention_layernorm.weight")),
+                wqkv=mv(torch.cat([w.pop(a + "q_proj.weight"), w.pop(a + "k_proj.weight"), w.pop(a + "v_proj.weight")], 0)),
+                bqkv=mv(torch.cat([w.pop(a + "q_proj.bias"), w.pop(a + "k_proj.bias"), w.pop(a + "v_proj.bias")], 0)),
+                wo=mv(w.pop(a + "o_proj.weight")),
+                wgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.weight"), w.pop(b + "mlp.up_proj.weight")], 0)),
+                wd=mv(w.pop(b + "mlp.down_proj.weight"))))
+        self.norm = mv(w.pop(lm + "norm.weight"))
+        self.lm_head = mv(w.pop("lm_head.weight"))
+
+    # ------------------------------------------------------------------ small helpers
+    def _rmsnorm(self, x, w, eps=1e-6):
+        out = torch.empty_like(x)
+        _abi.rmsnorm(x, w, out, eps)
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ ViT (vision_forward.py:57-101)
+    def vision_forward(self, pixels: torch.Tensor, grid, taps=None):
+        g = self.geo
+        grid = tuple(int(x) for x in grid)
+        plan = self._vit_plans.get(grid)
+        if plan is None:
+            plan = self._vit_plans[grid] = _VitPlan(grid, g, self.device)
+        n, unit = plan.n, g.spatial_merge_size ** 2
+        heads, hd = g.vit_heads, g.vit_hidden // g.vit_heads
+        x = F.linear(pixels.to(torch.bfloat16), self.w_patch)
+        x = x.reshape(n // unit, unit, -1)[plan.order].reshape(n, -1)
+        for li, b in enumerate(self.vit):
+            cu = plan.cu_full if li in g.fullatt_block_indexes else plan.cu_window
+            h = self._rmsnorm(x, b["n1"])
+            qkv = F.linear(h, b["wqkv"], b["bqkv"])
+            _abi.vit_rope(qkv, plan.cos, plan.sin, n, heads, hd)
+            o = torch.empty(n, heads, hd, dtype=torch.bfloat16, device=self.device)
+            _abi.vit_attn(qkv, cu, o, n, heads, hd, hd ** -0.5)
+            self.launches += 2
+            x = x + F.linear(o.view(n, -1), b["wproj"], b["bproj"])
+            h = self._rmsnorm(x, b["n2"])
+            gu = F.linear(h, b["wgu"], b["bgu"])
+            x = x + F.linear(F.silu(gu[:, :g.vit_mlp]) * gu[:, g.vit_mlp:], b["wd"], b["bd"])
+            if taps is not None:
+                taps.setdefault("vit_hidden", []).append(x)
+        h = self._rmsnorm(x, self.merger["ln"]).view(n // unit, -1)
+        y = torch.empty(n // unit, self.merger["w0"].shape[0], dtype=torch.bfloat16, device=self.device)
+        _abi.gemm_bf16(h, self.merger["w0"], self.merger["b0"], y, act=1)
+        out = torch.empty(n // unit, g.hidden, dtype=torch.bfloat16, device=self.device)
+        _abi.gemm_bf16(y, self.merger["w2"], self.merger["b2"], out, act=0, out_rows=plan.out_rows)
+        self.launches += 2
+        return out
+
+    # ------------------------------------------------------------------ LLM layers (language_forward.py:143-305)
+    def _layer(self, x, li, t, start, kv_len, splits, decode, taps=None):
+        g, c, L = self.geo, self.cache, self.layers[li]
+        hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
+        h = self._rmsnorm(x, L["ln1"], g.rms_eps)
+        qkv = F.linear(h, L["wqkv"], L["bqkv"])
+        q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+        q_rot = torch.empty(t, hq, d, dtype=torch.bfloat16, device=self.device)
+        if decode:
+            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, 0, None, c.cos_table, c.sin_table, c.section,
+                                 start_dev=self.kv_len_dev, text_pos_dev=c.next_pos)
+        else:
+            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, start, c.pos, c.cos_table, c.sin_table, c.section)
+        o = torch.empty(t, hq, d, dtype=torch.bfloat16, device=self.device)
+        _abi.attn_causal(c.view, c.cur, li, q_rot, o, t, hq, kv_len, self.scale, splits, self.ws if splits > 1 else None,
+                         kv_len_dev=self.kv_after_dev if decode else None)
+        self.launches += 2 + (1 if splits > 1 else 0)
+        if taps is not None:
+            taps.setdefault("attn_out", []).append(o.view(t, -1))
+            taps.setdefault("q_rot", []).append(q_rot)
+        x = x + F.linear(o.view(t, -1), L["wo"])
+        h = self._rmsnorm(x, L["ln2"], g.rms_eps)
+        gu = F.linear(h, L["wgu"])
+        return x + F.linear(F.silu(gu[:, :g.mlp]) * gu[:, g.mlp:], L["wd"])
+
+    def _logits(self, x_last):
+        h = self._rmsnorm(x_last, self.norm, self.geo.rms_eps)
+        logits = F.linear(h, self.lm_head).float()
+        if self.suppress is not None:
+            logits = logits.masked_fill(self.suppress, float("-inf"))
+        return logits
+
+    def prefill(self, new_ids, video_embeds, taps=None):
+        """Forward over the uncached ids (already uploaded as the tail of `cache.ids_dev`, positions in `cache.pos`)."""
+        c, g = self.cache, self.geo
+        t, start = len(new_ids), c.seq_len
+        if start + t > c.capacity:
+            raise RuntimeError(f"sequence of {start + t} tokens exceeds the arena capacity {c.capacity}")
+        x = F.embedding(c.ids_dev[start:start + t], self.embed)
+        if video_embeds is not None:
+            ids_np = np.asarray(new_ids)
+            where = np.flatnonzero(ids_np == VIDEO_PAD)
+            if where.size != video_embeds.shape[0]:
+                raise ValueError(f"Video features and video tokens do not match: tokens: {where.size}, features {video_embeds.shape[0]}")
+            brk = np.flatnonzero(np.diff(where) != 1) + 1
+            o = 0
+            for a, b in zip(np.concatenate([[0], brk]), np.concatenate([brk, [where.size]])):
+                x[where[a]:where[a] + (b - a)] = video_embeds[o:o + (b - a)]
+                o += b - a
+        splits = self.prefill_splits or (1 if (-(-t // (128 // g.group))) * g.num_kv_heads >= 74 or start + t < 2048 else 2)
+        for li in range(g.num_layers):
+            x = self._layer(x, li, t, start, start + t, splits, False, taps)
+        c.seq_len = start + t
+        c._seen_tokens += t
+        logits = self._logits(x[-1:])
+        if taps is not None:
+            taps["logits"] = logits[0]
+        return logits
+
+    # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
+    def _decode_body(self):
+        c, g = self.cache, self.geo
+        torch.add(self.kv_len_dev, 1, out=self.kv_after_dev)
+        x = F.embedding(self.tok_dev, self.embed)
+        for li in range(g.num_layers):
+            x = self._layer(x, li, 1, 0, c.capacity, self.decode_splits, True)
+        logits = self._logits(x)
+        self.tok_dev.copy_(torch.argmax(logits, dim=-1))
+        self.kv_len_dev.add_(1)
+        c.next_pos.add_(1)
+
+    def decode_step(self):
+        """Consumes `tok_dev`, appends its K/V, leaves the next greedy token in `tok_dev`."""
+        c = self.cache
+        if c.seq_len + 1 > c.capacity:
+            raise RuntimeError(f"arena capacity {c.capacity} exceeded during decode")
+        if self.use_graph:
+            gr = self._graphs.get(c.cur)
+            if gr is None:
+                # warm up once outside capture (cuBLAS workspaces, lazy kernel loading), then restore the state it advanced
+                saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone())
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._decode_body()
+                torch.cuda.current_stream().wait_stream(s)
+                self.kv_len_dev.copy_(saved[0]); c.next_pos.copy_(saved[1]); self.tok_dev.copy_(saved[2])
+                torch.cuda.synchronize()
+                before = self.launches
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._decode_body()
+                self._graph_launches = self.launches - before
+                self.launches = before
+                self._graphs[c.cur] = gr
+            gr.replay()
+            self.launches += self._graph_launches
+        else:
+            self._decode_body()
+        c.seq_len += 1
+        c._seen_tokens += 1
+
+    def generate(self, ids_full, pixels, grid, taps=None, forced=None):
+        """`model.generate` of the reference for one chunk: ViT + prefill + <= max_new_tokens greedy tokens.
+        `forced` (teacher forcing, the reference's --gt_json idea, inference.py:231-239): token j of the chunk is
+        taken from this list instead of the argmax; the argmax is still recorded in `self.last_argmax`."""
+        c = self.cache
+        input_len = len(ids_full)
+        new_ids = ids_full[c.seq_len:]
+        video = self.vision_forward(pixels, grid, taps) if pixels is not None else None
+        if taps is not None and video is not None:
+            taps["video_embeds"] = video
+        logits = self.prefill(new_ids, video, taps)
+        self.tok_dev.copy_(torch.argmax(logits, dim=-1))
+        self.kv_len_dev.fill_(c.seq_len)
+        seq = list(ids_full)
+        n_fwd = 1
+        self.last_argmax = []
+        while True:
+            self.tok_pinned.copy_(self.tok_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            tok = int(self.tok_pinned[0])
+            self.last_argmax.append(tok)
+            if forced is not None and len(self.last_argmax) <= len(forced) and forced[len(self.last_argmax) - 1] != tok:
+                tok = int(forced[len(self.last_argmax) - 1])
+                self.tok_dev.fill_(tok)
+            seq.append(tok)
+            if tok == IM_END or len(seq) - input_len >= self.max_new_tokens:
+                break
+            self.decode_step()
+            n_fwd += 1
+        return seq, n_fwd
+
+    # ------------------------------------------------------------------ session loop (inference.py:309-517)
+    def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None):
+        i, c = self.i, self.cache
+        if sync_timing:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        runs, plan = None, None
+        if self.prev_ids is not None:
+            plan = plan_past_kv(self.prev_ids, i, self.text_round, self.window_size, self.history, self.asb, self.aeb,
+                                self.clips, self.pixels, self.text_sink, self.text_sliding_window)
+            prev = plan.ids.tolist()
+            runs = plan.runs(c.seq_len)
+        else:
+            prev = None
+        self.clips.append(None)
+        if i == 0:
+            self.history = [{"role": "previous text", "content": previous_text},
+                            {"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"},
+                                                         {"type": "text", "text": "query"}]}]
+        else:
+            self.history.append({"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}]})
+        prompt = [int(t) for t in prompt_ids]
+        ids = prompt if prev is None else prev + (prompt if prev[-1] != LF else prompt[1:])
+        self.pixels.append(None)
+        self.grids.append(tuple(int(x) for x in grid))
+        n_vid = int(np.count_nonzero(np.asarray(ids) == TOKEN_IDS["<|vision_start|>"]))
+        want = self.grids[:max(n_vid, 1)]
+        if getattr(self, "_grids_uploaded", None) != want:
+            c.set_video_grids(want)
+            self._grids_uploaded = list(want)
+        c.compute_positions(ids)
+        self.launches += 1
+        if runs is not None and not (len(runs) == 1 and runs[0] == (0, 0, c.seq_len)):
+            c.compact(runs)
+            self.launches += 1
+        if sync_timing:
+            torch.cuda.synchronize()
+        t_pkv = time.perf_counter() - t0
+
+        t0 = time.perf_counter()
+        seq, n_fwd = self.generate(ids, pixels, grid, taps, forced)
+        if sync_timing:
+            torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        input_len = len(ids)
+        if seq[-1] != IM_END:
+            seq.append(IM_END)
+        new_tokens = seq[input_len:]
+        self.prev_ids = np.asarray(seq, dtype=np.int64)
+        self.history.append({"role": "assistant", "content": " ".join(str(t) for t in new_tokens) + " ..."})
+        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens)})
+        self.i += 1
+        return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "runs": runs, "cache_len": c.seq_len}

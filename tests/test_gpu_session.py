@@ -1,0 +1,93 @@
+"""GPU parity, BASELINE config 1: tiny random-init Qwen2.5-VL-architecture model streaming 64 synthetic
+448x448 frames (32 one-second chunks: 16 without eviction, 16 with) through sink / text-window /
+vision-window eviction, CUDA engine vs the CPU oracle in lock step.
+
+Per chunk:  gather runs, pruned ids and position ids bit-exact; K_rot bit-exact w.r.t. the reference
+mRoPE of the arena's own K_raw; per-layer attention outputs and last-position logits within a bf16
+tolerance; greedy token ids identical, where a differing argmax is tolerated only if the oracle's own
+margin between the two candidates is below the logit tolerance (the stream is then teacher-forced with
+the oracle's token, the reference's --gt_json mechanism, so that one near-tie cannot fork the stream).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import positions as o_pos
+from oracle.model import Session
+from streaming_vlm_b200 import synthetic
+from streaming_vlm_b200.config import TINY
+from tests.stream_sim import rle
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.08        # |logit| ~ 1; bf16 hidden state (8 mantissa bits) through a 512-wide lm_head
+ATTN_TOL = dict(rtol=3e-2, atol=2e-2)
+
+
+def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, check_every=1):
+    from streaming_vlm_b200.engine import StreamingEngine
+    geo = TINY
+    w_cpu = synthetic.random_weights(geo, seed=0)
+    suppress = synthetic.suppress_mask(geo.vocab)
+    oracle = Session(w_cpu, geo.as_dict(), window, text_round, sink, sliding, suppress=suppress)
+    engine = StreamingEngine({k: v.clone() for k, v in w_cpu.items()}, geo, capacity=8192, window_size=window,
+                             text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress)
+    n_vis = (height // 28) * (width // 28)
+    mismatches, total, prev_cache_len = 0, 0, 0
+    for i in range(n_chunks):
+        px, grid = synthetic.patchify(synthetic.frames(i, height, width), geo)
+        prompt = synthetic.round_prompt(i, n_vis, n_prev)
+        taps_o, taps_g = {}, {}
+        deep = (i % check_every == 0) or i == n_chunks - 1
+        ro = oracle.step(prompt, px.to(torch.bfloat16), grid, taps=taps_o if deep else None)
+        rg = engine.step(prompt, px.to("cuda"), grid, taps=taps_g if deep else None, forced=ro["new_tokens"])
+        # ---- integer state: bit-exact
+        assert rg["ids"] == ro["ids"], f"chunk {i}: ids"
+        assert rg["input_len"] == ro["input_len"] and rg["cache_len"] == ro["cache_len"], f"chunk {i}"
+        if ro["gather"] is not None:
+            want = [x for x in ro["gather"] if x < prev_cache_len]
+            got = [s_ + k for s_, _, l in rg["runs"] for k in range(l)]
+            assert got == want, f"chunk {i}: gather {rle(got)} vs {rle(want)}"
+        prev_cache_len = ro["cache_len"]
+        if deep:
+            n = rg["input_len"]
+            pos_ref = taps_o["position_ids"][:, 0, :].numpy()
+            # engine positions cover ids of the prefill; decode tokens continue the text run
+            pos_got = engine.cache.pos[:, :n].cpu().numpy().astype(np.float32)
+            assert np.array_equal(pos_got, pos_ref[:, :n]), f"chunk {i}: positions"
+            # K_rot == reference mRoPE applied to the arena's own K_raw at those positions (bit-exact)
+            k_raw, k_rot, _ = engine.cache.planes(0)
+            cos, sin = o_pos.rotary_cos_sin(taps_o["position_ids"][:, :, :n], o_pos.default_inv_freq(128, 1e6))
+            kr = k_raw[:, :n].cpu()
+            _, ref_rot = o_pos.apply_mrope(kr[None, :1, :1], kr[None], cos, sin, geo.mrope_section)
+            assert torch.equal(k_rot[:, :n].cpu().view(torch.int16), ref_rot[0].view(torch.int16)), f"chunk {i}: K_rot"
+            # floating point rows
+            torch.testing.assert_close(taps_g["video_embeds"].float().cpu(), taps_o["video_embeds"].float(), rtol=5e-2, atol=5e-2)
+            for li in range(geo.num_layers):
+                torch.testing.assert_close(taps_g["attn_out"][li].float().cpu(), taps_o["attn_out"][li].float(), **ATTN_TOL)
+            lg, lo = taps_g["logits"].cpu(), taps_o["logits"]
+            keep = ~suppress
+            assert (lg[keep] - lo[keep]).abs().max() < LOGIT_TOL, f"chunk {i}: logits {(lg[keep] - lo[keep]).abs().max()}"
+        # ---- greedy ids
+        for j, (tg, to) in enumerate(zip(engine.last_argmax, ro["new_tokens"])):
+            total += 1
+            if tg != to:
+                mismatches += 1
+                lo = ro["step_logits"][j]
+                assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]}"
+    return mismatches, total, engine, oracle
+
+
+def test_tiny_stream_small_windows():
+    """Fast: 112x112 frames (16 vision tokens / chunk), window 4, text_round 4, sink 16, window 24 -> every
+    eviction branch (move, user block drop, previous-text trim) is exercised within 20 chunks."""
+    mism, total, engine, _ = _run(20, 112, 112, 4, 4, 16, 24, 6)
+    assert engine.cache.compactions >= 14
+    assert mism <= max(2, total // 20), (mism, total)
+
+
+def test_tiny_stream_config1():
+    """BASELINE.json configs[0]: 64 frames of 448x448 = 32 chunks, defaults 16/16/512/512."""
+    mism, total, engine, oracle = _run(32, 448, 448, 16, 16, 512, 512, 24, check_every=4)
+    assert engine.cache.compactions >= 15
+    assert mism <= max(2, total // 20), (mism, total)
