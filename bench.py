@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the StreamingVLM hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one steady-state 1-second chunk of ONE video stream through the whole path: eviction
+(sink / text-window / vision-window compaction + contiguous-RoPE re-rotation), ViT on 2 new 448x448
+frames, chunk prefill of the ~300 uncached tokens against the ~5.5k-token pruned cache, and 20 greedily
+decoded commentary tokens, on a random-init Qwen2.5-VL-7B-architecture model in bf16.  The session is put
+into the steady state of a long stream (round 200 of the default 16/16/512/512 policy) by replaying the
+host-side bookkeeping and filling the arena; nothing inside the timed region is skipped.
+
+N > 1 (torchrun): every rank runs its own independent stream (no data-path collective; the reference's
+one-process-per-GPU sharding, eval/livesports3kcc/distributed_generate_streaming.py:53-62) -> weak scaling.
+
+`--impl reference`: the reference's path restated on the CPU (the oracle port; the reference itself cannot be
+imported here) on the host cores, per step a bounded, layer-count-scaled sample of the same chunk.
+"""
+import argparse
+import copy
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC, UNIT = "steady_state_frames_per_s", "frames/s"
+FRAMES_PER_CHUNK = 2
+STEADY_ROUNDS = 200
+NEW_TOKENS = 20
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]), "reasons": reasons,
+                "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_chunk_sample(n_threads, llm_layers=4, vit_blocks=8, decode_tokens=2, steps=1, warmup=0, budget_s=240.0):
+    """The reference path (oracle port) on the host cores: steady-state chunk, layer-count-scaled sample.
+    Returns (frames/s estimate, description, per-step chunk-time list)."""
+    from oracle.cache import ListCache
+    from oracle.model import Session
+    from streaming_vlm_b200 import synthetic
+    from streaming_vlm_b200.config import QWEN25VL_7B as G7
+    torch.set_num_threads(n_threads)
+    geo = G7.as_dict()
+    geo["num_layers"], geo["vit_depth"] = llm_layers, vit_blocks
+    geo["fullatt_block_indexes"] = [vit_blocks - 1]            # 1 full-attention block in 8, as 4 in 32
+    w = synthetic.block_weights_cpu(G7, seed=0, layers=llm_layers, vit_blocks=vit_blocks)
+    state = synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS)
+    sess = Session(w, geo, max_new_tokens=1 + decode_tokens, suppress=synthetic.suppress_mask(G7.vocab))
+    sess.prev_ids = torch.tensor([state["prev_ids"]], dtype=torch.long)
+    sess.history, sess.clips, sess.pixels = state["history"], state["clips"], state["pixels"]
+    sess.grids, sess.i = list(state["grids"]), state["i"]
+    n = state["cache_len"]
+    g = torch.Generator().manual_seed(1)
+    sess.cache = ListCache()
+    for _ in range(llm_layers):
+        sess.cache.key_cache.append((torch.randn(1, G7.num_kv_heads, n, 128, generator=g) * 0.5).to(torch.bfloat16))
+        sess.cache.value_cache.append((torch.randn(1, G7.num_kv_heads, n, 128, generator=g) * 0.5).to(torch.bfloat16))
+    times = []
+    t_start = time.perf_counter()
+    for s in range(warmup + steps):
+        i = sess.i
+        # keep the stream in steady state: generated text of the sample chunk is padded to NEW_TOKENS below
+        px, grid = synthetic.patchify(synthetic.frames(i), G7, dtype=torch.bfloat16)
+        r = sess.step(synthetic.round_prompt(i), px, grid)
+        tm = sess.timing[-1]
+        lscale = G7.num_layers / llm_layers
+        vit = (tm["vit_total"] - tm["vit_blocks"]) + tm["vit_blocks"] * (G7.vit_depth / vit_blocks)
+        prefill = tm["prefill_layers"] * lscale
+        dec_layers = tm["decode_layers"] / max(tm["n_decode_layers"], 1) * lscale
+        # non-layer parts of a forward (embedding, positions, final norm, lm_head): GEN minus the timed layer parts
+        other = max(tm["GEN"] - tm["vit_total"] - tm["prefill_layers"] - tm["decode_layers"], 0.0) / tm["n_forward"]
+        chunk = tm["PKV"] * lscale + vit + prefill + other + (NEW_TOKENS - 1) * (dec_layers + other)
+        if s >= warmup:
+            times.append(chunk)
+        # pad this round's generated text to NEW_TOKENS so that the next round sees a steady-state sequence
+        seq = sess.prev_ids.flatten().tolist()
+        pad = NEW_TOKENS - (len(r["new_tokens"]) - 1)
+        if pad > 0:
+            seq = seq[:-1] + synthetic._text_tokens(pad, 991 + i) + [seq[-1]]
+            sess.prev_ids = torch.tensor([seq], dtype=torch.long)
+            for li in range(llm_layers):
+                sess.cache.key_cache[li] = torch.cat([sess.cache.key_cache[li], sess.cache.key_cache[li][:, :, -pad:]], dim=2)
+                sess.cache.value_cache[li] = torch.cat([sess.cache.value_cache[li], sess.cache.value_cache[li][:, :, -pad:]], dim=2)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    chunk = statistics.median(times)
+    desc = (f"1 steady-state chunk (S~{n}): eviction + ViT + prefill + {decode_tokens} of {NEW_TOKENS - 1} decode forwards, timed on "
+            f"{llm_layers}/{G7.num_layers} LLM layers and {vit_blocks}/{G7.vit_depth} ViT blocks (1 full-attention) and scaled by layer "
+            f"count; embedding/merger/lm_head full size; {len(times)} timed step(s), median")
+    return FRAMES_PER_CHUNK / chunk, desc, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    value, desc, times = cpu_chunk_sample(cores, steps=steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "configs[1]: Qwen2.5-VL-7B-architecture random-init, single stream per GPU, 2 fps 448x448 synthetic video, "
+                        "steady state of the sink512/text-window512/vision-window16 policy (round 200, S~5.8k), per-second "
+                        "commentary decode of 20 tokens, greedy",
+            "chunk": {"frames": FRAMES_PER_CHUNK, "vit_tokens": 1024, "llm_vision_tokens": 256, "new_tokens": NEW_TOKENS},
+            "policy": {"window_size": 16, "text_round": 16, "text_sink": 512, "text_sliding_window": 512},
+            "cache_flush": "inputs larger than L2 (15 GB of weights and a 0.33 GB KV working set are swept every step)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_rooflines(engine, pk):
+    """Per-kernel achieved throughput, CUDA events around a CUDA-graph replay of repeated launches (so that host
+    launch gaps are not measured).  Algorithmic work per launch as defined in SURVEY.md section 8(d) / DESIGN.md."""
+    from streaming_vlm_b200 import _abi
+    g, c = engine.geo, engine.cache
+    dev = engine.device
+    out = {}
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return statistics.median(ts)
+
+    n = c.seq_len
+    hq, d, L = g.num_heads, g.head_dim, g.num_layers
+    # decode attention: one launch pair (split kernel + merge) per layer, N*2048 B per layer for 7B
+    q1 = torch.randn(1, hq, d, device=dev).to(torch.bfloat16)
+    o1 = torch.empty_like(q1)
+    engine.kv_after_dev.fill_(n)
+
+    def dec():
+        for li in range(L):
+            _abi.attn_causal(c.view, c.cur, li, q1, o1, 1, hq, c.capacity, engine.scale, engine.decode_splits, engine.ws,
+                             kv_len_dev=engine.kv_after_dev)
+    t = timed(dec) / L
+    byt = n * 2 * g.num_kv_heads * d * 2
+    out["attn_decode(split-KV+merge)"] = {"bound": "hbm", "achieved": byt / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                          "us_per_launch": t * 1e6, "launches_per_step": L * (NEW_TOKENS - 1), "kv_len": n}
+    # prefill attention
+    tq = 300
+    qp = torch.randn(tq, hq, d, device=dev).to(torch.bfloat16)
+    op = torch.empty_like(qp)
+    sp = engine.prefill_splits or 2
+
+    def pre():
+        for li in range(L):
+            _abi.attn_causal(c.view, c.cur, li, qp, op, tq, hq, n, engine.scale, sp, engine.ws)
+    t = timed(pre) / L
+    fl = 4.0 * tq * (n - tq / 2) * d * hq
+    out["attn_prefill"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                           "us_per_launch": t * 1e6, "launches_per_step": L, "tq": tq, "kv_len": n, "splits": sp}
+    # compaction + RoPE (identity gather of the n live rows; ping-pong twice per replay)
+    def comp():
+        _abi.kv_compact_rope(c.view, c.cur, [(0, 0, n)], c.pos, c.cos_table, c.sin_table, c.section)
+        _abi.kv_compact_rope(c.view, c.cur ^ 1, [(0, 0, n)], c.pos, c.cos_table, c.sin_table, c.section)
+    t = timed(comp) / 2
+    byt = 2.5 * n * g.kv_bytes_per_token     # read K_raw+V, write K_raw+K_rot+V
+    out["kv_compact_rope"] = {"bound": "hbm", "achieved": byt / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "us_per_launch": t * 1e6, "launches_per_step": 1, "tokens": n}
+    # ViT attention (windowed, 16 windows of 64) and patch merger GEMMs
+    heads, hd = g.vit_heads, g.vit_hidden // g.vit_heads
+    qkv = torch.randn(1024, 3, heads, hd, device=dev).to(torch.bfloat16)
+    ov = torch.empty(1024, heads, hd, dtype=torch.bfloat16, device=dev)
+    cu_w = torch.arange(0, 1025, 64, dtype=torch.int32, device=dev)
+    cu_f = torch.tensor([0, 1024], dtype=torch.int32, device=dev)
+    t = timed(lambda: [_abi.vit_attn(qkv, cu_w, ov, 1024, heads, hd, hd ** -0.5) for _ in range(8)]) / 8
+    out["vit_attn_window"] = {"bound": "tensor", "achieved": 4.0 * 16 * 64 * 64 * hd * heads / t / 1e12, "peak": pk["bf16_burst"],
+                              "unit": "TFLOP/s", "us_per_launch": t * 1e6, "launches_per_step": g.vit_depth - len(g.fullatt_block_indexes)}
+    t = timed(lambda: [_abi.vit_attn(qkv, cu_f, ov, 1024, heads, hd, hd ** -0.5) for _ in range(8)]) / 8
+    out["vit_attn_full"] = {"bound": "tensor", "achieved": 4.0 * 1024 * 1024 * hd * heads / t / 1e12, "peak": pk["bf16_burst"],
+                            "unit": "TFLOP/s", "us_per_launch": t * 1e6, "launches_per_step": len(g.fullatt_block_indexes)}
+    a = torch.randn(256, 5120, device=dev).to(torch.bfloat16)
+    y = torch.empty(256, 5120, dtype=torch.bfloat16, device=dev)
+    t = timed(lambda: [_abi.gemm_bf16(a, engine.merger["w0"], engine.merger["b0"], y, 1) for _ in range(8)]) / 8
+    out["patch_merger_gemm0"] = {"bound": "tensor", "achieved": 2.0 * 256 * 5120 * 5120 / t / 1e12, "peak": pk["bf16_burst"],
+                                 "unit": "TFLOP/s", "us_per_launch": t * 1e6, "launches_per_step": 1}
+    for k, v in out.items():
+        v["frac"] = v["achieved"] / v["peak"]
+        v["traffic"] = None
+        v["share_ms_per_step"] = v["us_per_launch"] * v["launches_per_step"] * 1e-3
+    return out
+
+
+def run_gpu(args):
+    from streaming_vlm_b200 import _abi, synthetic
+    from streaming_vlm_b200.config import QWEN25VL_7B as G7
+    from streaming_vlm_b200.engine import StreamingEngine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _abi.build()
+    dev = torch.device("cuda", local)
+    pk = peaks()
+
+    w = synthetic.random_weights(G7, seed=rank, device=dev)
+    engine = StreamingEngine(w, G7, capacity=8192, device=dev, suppress=synthetic.suppress_mask(G7.vocab))
+    del w
+    state = synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS, seed=rank)
+    engine.load_state(state, seed=rank)
+    total = args.warmup + 2 * args.steps + 1
+    base_i = engine.i
+    px_host = []
+    for k in range(total):
+        p, grid = synthetic.patchify(synthetic.frames(base_i + k), G7, dtype=torch.float32)
+        px_host.append(p.pin_memory())
+    px_dev = [p.to(dev) for p in px_host[:args.warmup + args.steps]]
+    prompts = [synthetic.round_prompt(base_i + k, seed=rank) for k in range(total)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(k0, n, host_pixels):
+        lat, toks = [], 0
+        for k in range(k0, k0 + n):
+            t0 = time.perf_counter()
+            px = px_host[k].to(dev, non_blocking=True) if host_pixels else px_dev[k]
+            r = engine.step(prompts[k], px, grid, sync_timing=False)
+            torch.cuda.current_stream().synchronize()
+            lat.append(time.perf_counter() - t0)
+            toks += min(len(r["new_tokens"]), NEW_TOKENS)
+        return lat, toks
+
+    run_steps(0, args.warmup, False)
+    # ---- timed region 1: inputs resident in HBM
+    barrier()
+    launches0 = engine.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        lat, toks = run_steps(args.warmup, args.steps, False)
+        e1.record()
+        barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = engine.launches - launches0
+    # ---- timed region 2: end to end, pixel values from pinned host memory, token ids read back every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    lat2, toks2 = run_steps(args.warmup + args.steps, args.steps, True)
+    f1.record()
+    barrier()
+    t_e2e = f0.elapsed_time(f1) * 1e-3
+    if dist is not None:
+        tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+
+    gen_s = sum(t["GEN"] for t in engine.timing[-args.steps:])
+    n_ids = len(engine.prev_ids)
+    h2d = px_host[0].numel() * 4 + n_ids * 8
+    d2h = NEW_TOKENS * 8
+    line = None
+    if rank == 0:
+        roofs = kernel_rooflines(engine, pk)
+        dom = max(roofs, key=lambda k: roofs[k]["share_ms_per_step"])
+        roof = {k: roofs[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+        roof["kernel"] = dom
+        roof["peak_source"] = pk["source"]
+        line = {"metric": METRIC, "value": world * args.steps * FRAMES_PER_CHUNK / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
+                "decode_tok_s": world * toks / t_dev, "p50_chunk_ms": 1e3 * statistics.median(lat), "p99_chunk_ms": 1e3 * max(lat),
+                "e2e": {"value": world * args.steps * FRAMES_PER_CHUNK / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "p50_chunk_ms": 1e3 * statistics.median(lat2), "decode_tok_s": world * toks2 / t_e2e},
+                "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "roofline_kernels": roofs,
+                "kv_len": engine.cache.seq_len, "streams_per_gpu": 1}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, desc, _ = cpu_chunk_sample(cores, steps=1, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

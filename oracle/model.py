@@ -60,12 +60,15 @@ def llm_layer(x, w, li, geo, cache, cos, sin, taps=None):
     return x + F.linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"])
 
 
-def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_grid=None, taps=None):
+def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_grid=None, taps=None, timers=None):
     """One forward over the uncached ids.  Returns fp32 logits of the last position."""
     ids_t = torch.tensor(new_ids, dtype=torch.long)
     x = F.embedding(ids_t, w["model.language_model.embed_tokens.weight"])
     if pixels is not None:
-        vid = vision_forward(pixels, pixel_grid, w, geo)
+        t0 = time.perf_counter()
+        vid = vision_forward(pixels, pixel_grid, w, geo, timers=timers)
+        if timers is not None:
+            timers["vit_total"] = timers.get("vit_total", 0.0) + time.perf_counter() - t0
         mask = ids_t == VIDEO_PAD
         if int(mask.sum()) != vid.shape[0]:
             raise ValueError(f"Video features and video tokens do not match: tokens: {int(mask.sum())}, features {vid.shape[0]}")
@@ -78,8 +81,13 @@ def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_gr
     cos, sin = rotary_cos_sin(pos, default_inv_freq(geo["head_dim"], geo["rope_theta"]), x.dtype)
     if taps is not None:
         taps["position_ids"] = pos
+    t0 = time.perf_counter()
     for li in range(geo["num_layers"]):
         x = llm_layer(x, w, li, geo, cache, cos, sin, taps)
+    if timers is not None:
+        key = "prefill_layers" if len(new_ids) > 1 else "decode_layers"
+        timers[key] = timers.get(key, 0.0) + time.perf_counter() - t0
+        timers["n_" + key] = timers.get("n_" + key, 0) + 1
     x = rmsnorm(x, w["model.language_model.norm.weight"], geo["rms_eps"])
     logits = F.linear(x[-1:], w["lm_head.weight"]).float()[0]
     if taps is not None:
@@ -136,6 +144,7 @@ class Session:
         input_len = len(ids)
 
         t0 = time.perf_counter()
+        timers = {}
         full = list(ids)                       # streaming_args.input_ids
         seq = list(ids)
         n_fwd = 0
@@ -145,7 +154,7 @@ class Session:
             new = seq[cached:]
             px = pixels if n_fwd == 0 else None
             logits = model_forward(new, full, self.grids, self.cache, self.w, self.geo, px, [tuple(grid)],
-                                   taps if n_fwd == 0 else None)
+                                   taps if n_fwd == 0 else None, timers)
             full = full + [0]                   # F.pad(ids, (0,1)) after every forward
             n_fwd += 1
             if self.suppress is not None:
@@ -161,7 +170,7 @@ class Session:
         new_tokens = seq[input_len:]
         self.prev_ids = torch.tensor([seq], dtype=torch.long)
         self.history.append({"role": "assistant", "content": " ".join(str(t) for t in new_tokens) + " ..."})
-        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens)})
+        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens), **timers})
         self.i += 1
         return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "gather": gather,
                 "cache_len": self.cache.get_seq_length(), "step_logits": step_logits}

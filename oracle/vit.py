@@ -101,7 +101,7 @@ def patch_merger(x, w, pfx="model.visual.merger.", unit=4):
     return F.linear(h, w[pfx + "mlp.2.weight"], w[pfx + "mlp.2.bias"])
 
 
-def vision_forward(pixels, grid_thw, w, geo, return_hidden=False):
+def vision_forward(pixels, grid_thw, w, geo, return_hidden=False, timers=None):
     """pixels [N, C*Tp*P*P], grid_thw list of (t,h,w) -> merged tokens [N/4, out_hidden]."""
     pfx = "model.visual."
     unit = geo["spatial_merge_size"] ** 2
@@ -120,6 +120,8 @@ def vision_forward(pixels, grid_thw, w, geo, return_hidden=False):
             full.append(full[-1] + h * ww)
     cu_full = torch.tensor(full, dtype=torch.int32)
     hidden = []
+    import time as _time
+    _t0 = _time.perf_counter()
     for li in range(geo["vit_depth"]):
         b = f"{pfx}blocks.{li}."
         cu = cu_full if li in geo["fullatt_block_indexes"] else cu_win
@@ -127,6 +129,8 @@ def vision_forward(pixels, grid_thw, w, geo, return_hidden=False):
         x = x + vit_mlp(rmsnorm(x, w[b + "norm2.weight"]), w, b + "mlp.")
         if return_hidden:
             hidden.append(x)
+    if timers is not None:
+        timers["vit_blocks"] = timers.get("vit_blocks", 0.0) + _time.perf_counter() - _t0
     merged = patch_merger(x, w, pfx + "merger.", unit)
     merged = merged[torch.argsort(widx)]
     return (merged, hidden) if return_hidden else merged

@@ -333,6 +333,25 @@ class StreamingEngine:
             n_fwd += 1
         return seq, n_fwd
 
+    def load_state(self, state, seed=0):
+        """Adopt the bookkeeping produced by `synthetic.fast_forward` and fill the arena with random K_raw / V for the
+        rows it implies (K_rot is then derived by the real kernel), i.e. jump to the steady state of a long stream."""
+        c = self.cache
+        n = int(state["cache_len"])
+        if n > c.capacity:
+            raise RuntimeError(f"state needs {n} cache rows, arena capacity is {c.capacity}")
+        self.prev_ids = np.asarray(state["prev_ids"], dtype=np.int64)
+        self.history, self.clips, self.pixels = state["history"], state["clips"], state["pixels"]
+        self.grids, self.i = list(state["grids"]), int(state["i"])
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        for plane in (0, 2):
+            c.arena[c.cur, plane, :, :, :n].normal_(0.0, 0.5, generator=g)
+        n_vid = int(np.count_nonzero(self.prev_ids[:n] == TOKEN_IDS["<|vision_start|>"]))
+        c.set_video_grids(self.grids[:max(n_vid, 1)])
+        self._grids_uploaded = None
+        c.seq_len = n
+        c.compact([(0, 0, n)], self.prev_ids[:n])
+
     # ------------------------------------------------------------------ session loop (inference.py:309-517)
     def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None):
         i, c = self.i, self.cache

@@ -134,3 +134,66 @@ def random_weights(geo: Geometry, seed: int = 0, device="cpu", dtype=torch.bfloa
                 else (s * torch.randn(shape, generator=g, dtype=torch.float32))
         w[name] = t.to(dtype)
     return w
+
+
+def block_weights_cpu(geo: Geometry, seed: int = 0, dtype=torch.bfloat16, layers=None, vit_blocks=None, block_elems=1 << 26):
+    """CPU state dict for the big geometries in seconds instead of minutes: one seeded normal(0,1) block is
+    generated once and every tensor is a scaled COPY of a different window of it (distinct memory, realistic
+    values).  `layers` / `vit_blocks` restrict the dict to the first n LLM layers / ViT blocks."""
+    g = torch.Generator().manual_seed(seed)
+    block = torch.randn(block_elems, generator=g, dtype=torch.float32).to(dtype)
+    w, off = {}, 0
+    for name, shape, kind in weight_shapes(geo):
+        if layers is not None and ".language_model.layers." in name and int(name.split(".layers.")[1].split(".")[0]) >= layers:
+            continue
+        if vit_blocks is not None and ".visual.blocks." in name and int(name.split(".blocks.")[1].split(".")[0]) >= vit_blocks:
+            continue
+        n = math.prod(shape)
+        t = torch.empty(n, dtype=dtype)
+        done = 0
+        while done < n:
+            take = min(n - done, block_elems - off)
+            t[done:done + take] = block[off:off + take]
+            done += take
+            off = (off + take) % block_elems
+        if kind == "n":
+            t = 1.0 + 0.1 * t
+        else:
+            s = 0.02 if (kind == "b" or "embed_tokens" in name) else min(0.04, 1.0 / math.sqrt(math.prod(shape[1:])))
+            t = t * s
+        w[name] = t.to(dtype).reshape(shape)
+    return w
+
+
+def fast_forward(rounds: int, window_size=16, text_round=16, text_sink=512, text_sliding_window=512, n_vision_tokens=256,
+                 previous_text_tokens=24, new_tokens=20, grid=(1, 32, 32), seed=0):
+    """Host-only replay of `rounds` chunks of session bookkeeping (ids, history, eviction planning) with
+    synthetic generated text, to put a session into its steady state without running the model.  Returns the
+    state a session object needs: prev_ids (incl. the forced <|im_end|>), history, clips, pixels, grids, i, and
+    cache_len (rows the cache holds for prev_ids)."""
+    from .inference.inference import plan_past_kv
+    hist, clips, pixels, grids = [], [], [], []
+    prev, cache_len = None, 0
+    for i in range(rounds):
+        if prev is not None:
+            plan = plan_past_kv(prev, i, text_round, window_size, hist, 3, 2, clips, pixels, text_sink, text_sliding_window)
+            cache_len = sum(r[2] for r in plan.runs(cache_len))
+            prev = plan.ids.tolist()
+        clips.append(None)
+        if i == 0:
+            hist[:] = [{"role": "previous text", "content": ""},
+                       {"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}, {"type": "text", "text": "query"}]}]
+        else:
+            hist.append({"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}]})
+        prompt = round_prompt(i, n_vision_tokens, previous_text_tokens, 8, seed)
+        ids = prompt if prev is None else prev + (prompt if prev[-1] != LF else prompt[1:])
+        pixels.append(None)
+        grids.append(tuple(grid))
+        gen = _text_tokens(new_tokens, seed * 7919 + 31 * i + 5)
+        seq = ids + gen
+        cache_len = len(seq) - 1
+        seq = seq + [IM_END]
+        prev = seq
+        hist.append({"role": "assistant", "content": " ".join(str(t) for t in gen + [IM_END]) + " ..."})
+    return {"prev_ids": prev, "history": hist, "clips": clips, "pixels": pixels, "grids": grids, "i": rounds,
+            "cache_len": cache_len}
