@@ -309,10 +309,14 @@ def run_gpu(args):
     launches0 = engine.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        if args.profile_range:
+            torch.cuda.profiler.start()
         e0.record()
         lat, toks = run_steps(args.warmup, args.steps, False)
         e1.record()
         barrier()
+        if args.profile_range:
+            torch.cuda.profiler.stop()
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = engine.launches - launches0
     # ---- timed region 2: end to end, pixel values from pinned host memory, token ids read back every step
@@ -366,6 +370,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around timed region 1 (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,8 @@ class StreamingCache:
         self.value_cache = _PlaneList(self, V_PLANE)
         self._rot_stale = False
         self.compactions = 0
+        self.decode_splits = max(1, min((self.capacity + 127) // 128, 148 // self.kv_heads))
+        self._pending_start = 0
 
     # ------------------------------------------------------------------ reference interface
     def get_seq_length(self, layer_idx: int = 0) -> int:
@@ -113,24 +115,28 @@ class StreamingCache:
                 self.position_ids_cache[layer_idx] = position_ids
         return self.position_ids_cache[layer_idx]
 
-    def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
-        """Append raw K / V `[1, H, T, D]` for one layer; returns the `[1, H, S, D]` views (reference :30-74).
-        K_rot for the new rows is NOT produced here -- the attention op does that (`svlm_qkv_rope_append`);
-        this method exists for callers that drive the cache the HF way."""
-        t = key_states.shape[-2]
-        base = self.seq_len if layer_idx > 0 else self.seq_len
-        start = self._pending_start if (layer_idx > 0 and hasattr(self, "_pending_start")) else base
+    def layer_start(self, layer_idx: int, t: int) -> int:
+        """Arena row at which layer `layer_idx` appends `t` new tokens.  All layers of one forward append at the
+        same row; the sequence length advances once the last layer's append has been enqueued."""
         if layer_idx == 0:
-            self._seen_tokens += t
             self._pending_start = self.seq_len
-            start = self.seq_len
+            self._seen_tokens += t
+        start = self._pending_start
         if start + t > self.capacity:
             raise RuntimeError(f"StreamingCache capacity {self.capacity} exceeded ({start + t})")
+        if layer_idx == self.layers - 1:
+            self.seq_len = start + t
+        return start
+
+    def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
+        """Append raw K / V `[1, H, T, D]` for one layer; returns the `[1, H, S, D]` views (reference :30-74).
+        K_rot for the new rows is NOT produced here (the attention op does that, `svlm_qkv_rope_append`);
+        this method exists for callers that drive the cache the HF way."""
+        t = key_states.shape[-2]
+        start = self.layer_start(layer_idx, t)
         self.arena[self.cur, K_RAW, layer_idx, :, start:start + t].copy_(key_states.reshape(self.kv_heads, t, self.head_dim))
         self.arena[self.cur, V_PLANE, layer_idx, :, start:start + t].copy_(value_states.reshape(self.kv_heads, t, self.head_dim))
         self._rot_stale = True
-        if layer_idx == self.layers - 1:
-            self.seq_len = start + t
         n = start + t
         return (self.arena[self.cur, K_RAW, layer_idx, :, :n].unsqueeze(0), self.arena[self.cur, V_PLANE, layer_idx, :, :n].unsqueeze(0))
 
@@ -143,6 +149,12 @@ class StreamingCache:
         self.n_grids = g.shape[0]
 
     def upload_ids(self, ids) -> int:
+        if isinstance(ids, torch.Tensor) and ids.is_cuda:
+            n = ids.numel()
+            if n > self.capacity:
+                raise RuntimeError(f"sequence of {n} tokens exceeds the arena capacity {self.capacity}")
+            self.ids_dev[:n].copy_(ids.reshape(-1))
+            return n
         ids = as_host_ids(ids)
         n = ids.shape[0]
         if n > self.capacity:

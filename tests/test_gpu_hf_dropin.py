@@ -1,0 +1,76 @@
+"""GPU: the drop-in boundary.  A stock transformers Qwen2_5_VLForConditionalGeneration (tiny, random init) is
+patched with `convert_qwen2_5_to_streaming` and driven exactly like the reference's session loop drives it
+(`inference/inference.py:319, 397-416, 440-451`): `process_past_kv` -> `model.generate(**inputs,
+past_key_values=..., streaming_args=...)`.  Checked against the CPU oracle run on the same weights."""
+import pytest
+import torch
+
+from oracle.model import Session
+from streaming_vlm_b200 import synthetic
+from streaming_vlm_b200.config import from_hf_config
+
+pytestmark = pytest.mark.gpu
+
+
+def test_patched_hf_model_matches_oracle():
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
+    from streaming_vlm_b200.inference.inference import process_past_kv
+    from streaming_vlm_b200.inference.qwen2_5.patch_model import convert_qwen2_5_to_streaming
+    from streaming_vlm_b200.inference.streaming_args import StreamingArgs
+    torch.manual_seed(0)
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(hidden_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, intermediate_size=1024,
+                         vocab_size=152064, rms_norm_eps=1e-6,
+                         rope_parameters={"rope_type": "default", "rope_theta": 1e6, "mrope_section": [16, 24, 24]}),
+        vision_config=dict(depth=4, hidden_size=320, num_heads=4, intermediate_size=640, out_hidden_size=512,
+                           fullatt_block_indexes=[1, 3], tokens_per_second=2))
+    model = Qwen2_5_VLForConditionalGeneration(cfg).to(torch.bfloat16).eval()
+    w_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    geo = from_hf_config(cfg)
+    assert geo.num_layers == 2 and geo.vit_depth == 4 and geo.tokens_per_second == 2
+    model = convert_qwen2_5_to_streaming(model.to("cuda"))
+    sup = synthetic.suppress_mask(geo.vocab)
+    win, tr, sink, slide = 2, 2, 8, 8
+    oracle = Session(w_cpu, geo.as_dict(), win, tr, sink, slide, suppress=sup, max_new_tokens=5)
+
+    args = StreamingArgs(pos_mode="shrink")
+    cache = StreamingCache(geo, capacity=1024, device="cuda")
+    history, clips, pixels = [], [], []
+    prev = None
+    for i in range(6):
+        px, grid = synthetic.patchify(synthetic.frames(i, 112, 112), geo)
+        prompt = synthetic.round_prompt(i, 16, 6)
+        ro = oracle.step(prompt, px.to(torch.bfloat16), grid)
+        # ---- the reference's loop body, product side
+        past = cache if prev is not None else None
+        past, prev, clips, pixels = process_past_kv(past, i, tr, win, history, prev, 3, 2, clips, pixels, sink, slide)
+        clips.append(None)
+        if i == 0:
+            history[:] = [{"role": "previous text", "content": ""},
+                          {"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}, {"type": "text", "text": "q"}]}]
+        else:
+            history.append({"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}]})
+        ids = torch.tensor([prompt], device="cuda")
+        if prev is not None:
+            ids = torch.cat([prev, ids if prev[0, -1].item() != 198 else ids[:, 1:]], dim=1)
+        pixels.append(None)
+        args.input_ids = ids
+        g = torch.tensor([list(grid)], device="cuda")
+        args.video_grid_thw = g if i == 0 else torch.cat([args.video_grid_thw, g], dim=0)
+        out = model.generate(input_ids=ids, pixel_values_videos=px.to("cuda"), video_grid_thw=g, past_key_values=cache,
+                             max_new_tokens=5, do_sample=False, streaming_args=args, suppress_tokens=sup.to("cuda"))
+        seq = out.sequences
+        if seq[0, -1].item() != 151645:
+            seq = torch.cat([seq, torch.tensor([[151645]], device="cuda")], dim=1)
+        new = seq[0, ids.shape[1]:].tolist()
+        prev = seq.clone()
+        history.append({"role": "assistant", "content": "x ..."})
+        assert cache.get_seq_length() == ro["cache_len"], f"chunk {i}"
+        # identical greedy ids unless the oracle's own margin is inside the bf16 logit tolerance
+        if new != ro["new_tokens"]:
+            j = next(k for k, (a, b) in enumerate(zip(new, ro["new_tokens"])) if a != b)
+            lo = ro["step_logits"][j]
+            assert lo[ro["new_tokens"][j]] - lo[new[j]] < 0.08, f"chunk {i} token {j}"
+            pytest.skip("near-tie forked the un-forced stream; covered by test_gpu_session with teacher forcing")
+    assert cache.compactions >= 3
