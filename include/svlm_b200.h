@@ -158,6 +158,26 @@ int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int 
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (7) Decode-step (one token) weight-streaming GEMV with fused RMSNorm prologue and epilogue; HBM-bound.
+ * Replaces, for q_len == 1: the nn.Linear / RMSNorm / SiLU / residual-add calls of
+ *           qwen2_5/language_forward.py:175-177 (q/k/v_proj after input_layernorm, :277), :255 (o_proj) + :290
+ *           (residual), :295-297 (post_attention_layernorm, MLP, residual), and :497 + qwen2_5/model_forward.py:317
+ *           (final norm + lm_head) followed by the greedy argmax of generate/streaming_generate_qwen.py:99.
+ *   W [rows][K] bf16 row-major (nn.Linear layout), x [K] bf16, y [N] bf16
+ *   norm_weight : if non-NULL, x is first replaced by HF RMSNorm(x) * norm_weight (eps)
+ *   mode 0: y = W x + bias            mode 1: y = residual + (W x + bias)      (y may alias residual)
+ *   mode 2: W = [gate rows ; up rows] (2N rows), y = silu(gate) * up
+ * svlm_lm_head_argmax: token_out = first index of the max bf16 logit over rows with suppress[row] == 0, then advances
+ * the decode loop's device counters (kv_len += 1, kv_after = kv_len + 1, next_pos += 1).  key_scratch: one zeroed
+ * uint64 owned by the caller.
+ * ------------------------------------------------------------------------------------- */
+int svlm_gemv_bf16(const void* W, const void* x, const void* norm_weight, float eps, const void* bias,
+                   const void* residual, void* y, int N, int K, int mode, void* stream);
+int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
+                        int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
+                        int32_t* next_pos, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (the reference-facing plugin call with HOST data):
  * copy in, run, copy out, synchronise.  Used by bench.py's end-to-end leg and by callers that
  * keep the cache in host memory.

@@ -16,14 +16,14 @@ import torch
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libsvlm_b200.so")
-SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "gemm.cu"]
+SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "gemm.cu", "gemv.cu"]
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "svlm_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_kv_compact_rope_host"]
+           "svlm_rmsnorm", "svlm_gemv_bf16", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
 
@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
     L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
     L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
     L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
+    L.svlm_gemv_bf16.argtypes = [vp, vp, vp, c_float, vp, vp, vp, c_int, c_int, c_int, vp]
+    L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -191,6 +193,21 @@ def gemm_bf16(a, w, bias, out, act: int = 0, out_rows=None):
     assert w.shape[1] == k and a.is_contiguous() and w.is_contiguous() and out.is_contiguous()
     check(lib().svlm_gemm_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k, act, _ptr(out_rows), _stream()),
           "svlm_gemm_bf16")
+
+
+def gemv_bf16(w, x, y, mode: int = 0, norm_weight=None, eps: float = 1e-6, bias=None, residual=None):
+    """y[N] = epilogue(W[rows, K] @ prologue(x[K])); mode 0 plain, 1 residual add, 2 SwiGLU (W = [gate; up])."""
+    _req_cuda(w, x, y)
+    n = y.numel()
+    check(lib().svlm_gemv_bf16(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(bias), _ptr(residual), y.data_ptr(), n,
+                               w.shape[1], mode, _stream()), "svlm_gemv_bf16")
+
+
+def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, kv_len, kv_after, next_pos):
+    _req_cuda(w, x, key_scratch, token_out)
+    check(lib().svlm_lm_head_argmax(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
+                                    key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
+                                    next_pos.data_ptr(), _stream()), "svlm_lm_head_argmax")
 
 
 def rmsnorm(x, weight, out, eps: float):

@@ -208,33 +208,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
         float m_run = -INFINITY, l_run = 0.f;
+        // a warp none of whose 32 rows is a real query row (decode: 3 of the 4 warps) only keeps the barriers moving
+        const bool warp_active = __any_sync(0xffffffffu, valid);
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
             const int kv0 = (my_begin + j) * BN;
             mbar_wait(&bars->s_full[b], (j >> 1) & 1);
             tc_fence_after();
+            if (!warp_active) {
+                tc_fence_before();
+                mbar_arrive(&bars->p_full[b]);
+                continue;
+            }
             uint32_t sr[4][32];
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + b * 128 + c * 32, sr[c]);
             tmem_wait_ld();
             const bool need_mask = (kv0 < lo) || (kv0 + BN > hi);
-            float mt = -INFINITY;
+            float mt_raw = -INFINITY;                      // max of the RAW scores (scale > 0 keeps the order)
+            if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(sr[c][i]) * p.scale_log2;
-                    if (need_mask) {
+                    for (int i = 0; i < 32; ++i) {
                         const int kv = kv0 + c * 32 + i;
-                        if (kv < lo || kv >= hi) x = -INFINITY;
+                        if (kv < lo || kv >= hi) sr[c][i] = 0xff800000u;   // -inf
+                        mt_raw = fmaxf(mt_raw, __uint_as_float(sr[c][i]));
                     }
-                    sr[c][i] = __float_as_uint(x);
-                    mt = fmaxf(mt, x);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mt_raw = fmaxf(mt_raw, __uint_as_float(sr[c][i]));
                 }
             }
+            const float mt = mt_raw * p.scale_log2;
             const bool upd = mt > m_run + RESCALE_THRESHOLD;      // also true for the first finite tile (m_run = -inf)
             const float m_new = upd ? mt : m_run;
-            const float alpha = upd ? exp2f(m_run - m_new) : 1.0f; // m_run = -inf -> 0
+            const float alpha = upd ? ex2_approx(m_run - m_new) : 1.0f; // m_run = -inf -> 0
             if (__any_sync(0xffffffffu, upd && j > 0)) {
                 // rescale the running O row; PV(j-1) must have landed first.  s_full(j) observed => PV(j-3) and
                 // everything older completed, so barrier (j-1)&1 is in one of exactly two states and the parity
@@ -251,21 +263,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_st32(tmem + lane_addr + 256 + c * 32, orow);
                 }
             }
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            float lsum = 0.f;
+            const float neg_m = (m_new == -INFINITY) ? 0.f : -m_new;
+            float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float p0 = exp2f(__uint_as_float(sr[c][2 * i]) - m_use);
-                    const float p1 = exp2f(__uint_as_float(sr[c][2 * i + 1]) - m_use);
-                    lsum += p0 + p1;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, neg_m));
+                    lsum0 += p0;
+                    lsum1 += p1;
                     pk[i] = pack_bf16(p0, p1);
                 }
                 tmem_st16(tmem + lane_addr + b * 128 + c * 16, pk);
             }
-            l_run = l_run * alpha + lsum;
+            l_run = l_run * alpha + (lsum0 + lsum1);
             m_run = m_new;
             tmem_wait_st();
             tc_fence_before();
@@ -282,7 +295,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t orow[32];
-            if (n_tiles > 0) {
+            if (n_tiles > 0 && warp_active) {
                 tmem_ld32(tmem + lane_addr + 256 + c * 32, orow);
                 tmem_wait_ld();
             } else {
@@ -322,20 +335,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // Merge of the split-KV partials: out = sum_s 2^(m_s - M) O_s / sum_s 2^(m_s - M) l_s.
-// grid = Tq * Hq, block = 128 (one thread per output column).
+// grid = Tq * Hq, block = 128 (one thread per output column).  The (m, l) pairs are fetched by all threads at once
+// and the per-split weights live in shared memory, so the column loop issues independent loads.
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
                                                             uint16_t* __restrict__ out, int rows, int D, int num_splits) {
-    const int r = blockIdx.x, d = threadIdx.x;
-    float M = -INFINITY;
-    for (int s = 0; s < num_splits; ++s) M = fmaxf(M, part_ml[(int64_t)s * rows + r].x);
-    float L = 0.f, acc = 0.f;
-    for (int s = 0; s < num_splits; ++s) {
+    __shared__ float w_s[256];
+    __shared__ float l_s[256];
+    __shared__ float red[4];
+    const int r = blockIdx.x, d = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m_loc = -INFINITY;
+    for (int s = d; s < num_splits; s += 128) {
         const float2 ml = part_ml[(int64_t)s * rows + r];
-        const float w = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - M);
-        L += w * ml.y;
-        if (d < D && w != 0.f) acc += w * part_o[((int64_t)s * rows + r) * D + d];
+        w_s[s] = ml.x;
+        l_s[s] = ml.y;
+        m_loc = fmaxf(m_loc, ml.x);
     }
-    if (d < D) out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m_loc = fmaxf(m_loc, __shfl_xor_sync(0xffffffffu, m_loc, o));
+    if (lane == 0) red[warp] = m_loc;
+    __syncthreads();
+    const float M = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float l_loc = 0.f;
+    for (int s = d; s < num_splits; s += 128) {
+        const float w = (w_s[s] == -INFINITY) ? 0.f : ex2_approx(w_s[s] - M);
+        w_s[s] = w;
+        l_loc += w * l_s[s];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l_loc += __shfl_xor_sync(0xffffffffu, l_loc, o);
+    if (lane == 0) red[warp] = l_loc;
+    __syncthreads();
+    const float L = red[0] + red[1] + red[2] + red[3];
+    if (d >= D) return;
+    float acc = 0.f;
+    const float* src = part_o + (int64_t)r * D + d;
+    const int64_t stride = (int64_t)rows * D;
+#pragma unroll 8
+    for (int s = 0; s < num_splits; ++s) acc += w_s[s] * src[s * stride];
+    out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
 }
 
 static int launch_attn(int mode, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,

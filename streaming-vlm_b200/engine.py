@@ -115,6 +115,12 @@ class StreamingEngine:
         self.tok_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.tok_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._graphs = {}
+        self._dec_qkv = torch.zeros((g.num_heads + 2 * g.num_kv_heads) * g.head_dim, dtype=torch.bfloat16, device=dev)
+        self._dec_q = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+        self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+        self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
+        self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.suppress_u8 = None if self.suppress is None else self.suppress.to(torch.uint8).contiguous()
         self._vit_plans = {}
         # session state (reference: inference.py:297-303)
         self.prev_ids = None
@@ -261,15 +267,28 @@ class StreamingEngine:
 
     # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
     def _decode_body(self):
+        """One decode forward, every op a kernel of libsvlm_b200.so except the embedding row lookup: per layer
+        norm+QKV GEMV -> rotate/append -> split-KV attention (+merge) -> o_proj GEMV + residual -> norm+gate/up GEMV
+        with SwiGLU -> down GEMV + residual; then final norm + lm_head GEMV + argmax + counter update."""
         c, g = self.cache, self.geo
-        torch.add(self.kv_len_dev, 1, out=self.kv_after_dev)
-        x = F.embedding(self.tok_dev, self.embed)
-        for li in range(g.num_layers):
-            x = self._layer(x, li, 1, 0, c.capacity, self.decode_splits, True)
-        logits = self._logits(x)
-        self.tok_dev.copy_(torch.argmax(logits, dim=-1))
-        self.kv_len_dev.add_(1)
-        c.next_pos.add_(1)
+        hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
+        x = F.embedding(self.tok_dev, self.embed)[0].contiguous()
+        qkv, q_rot, o, act = self._dec_qkv, self._dec_q, self._dec_o, self._dec_act
+        q2 = qkv.view(1, -1)
+        q, k, v = q2[:, :hq * d], q2[:, hq * d:(hq + hkv) * d], q2[:, (hq + hkv) * d:]
+        for li, L in enumerate(self.layers):
+            _abi.gemv_bf16(L["wqkv"], x, qkv, 0, L["ln1"], g.rms_eps, L["bqkv"])
+            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, 1, hq, q_rot, 0, None, c.cos_table, c.sin_table, c.section,
+                                 start_dev=self.kv_len_dev, text_pos_dev=c.next_pos)
+            _abi.attn_causal(c.view, c.cur, li, q_rot, o, 1, hq, c.capacity, self.scale, self.decode_splits,
+                             self.ws if self.decode_splits > 1 else None, kv_len_dev=self.kv_after_dev)
+            _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
+            _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
+            _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
+        self.launches += g.num_layers * (6 + (1 if self.decode_splits > 1 else 0))
+        _abi.lm_head_argmax(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
+                            self.kv_len_dev, self.kv_after_dev, c.next_pos)
+        self.launches += 2
 
     def decode_step(self):
         """Consumes `tok_dev`, appends its K/V, leaves the next greedy token in `tok_dev`."""
@@ -280,13 +299,13 @@ class StreamingEngine:
             gr = self._graphs.get(c.cur)
             if gr is None:
                 # warm up once outside capture (cuBLAS workspaces, lazy kernel loading), then restore the state it advanced
-                saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone())
+                saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone(), self.kv_after_dev.clone())
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._decode_body()
                 torch.cuda.current_stream().wait_stream(s)
-                self.kv_len_dev.copy_(saved[0]); c.next_pos.copy_(saved[1]); self.tok_dev.copy_(saved[2])
+                self.kv_len_dev.copy_(saved[0]); c.next_pos.copy_(saved[1]); self.tok_dev.copy_(saved[2]); self.kv_after_dev.copy_(saved[3])
                 torch.cuda.synchronize()
                 before = self.launches
                 gr = torch.cuda.CUDAGraph()
@@ -315,6 +334,7 @@ class StreamingEngine:
         logits = self.prefill(new_ids, video, taps)
         self.tok_dev.copy_(torch.argmax(logits, dim=-1))
         self.kv_len_dev.fill_(c.seq_len)
+        self.kv_after_dev.fill_(c.seq_len + 1)
         seq = list(ids_full)
         n_fwd = 1
         self.last_argmax = []

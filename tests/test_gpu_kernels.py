@@ -292,3 +292,63 @@ def test_vit_rope_and_attention(abi, heads, D, n, cu):
     torch.cuda.synchronize()
     ref = o_attn.varlen_attention(q_ref, k_ref, qkv[:, 2], cu)
     torch.testing.assert_close(out.cpu().float(), ref.float(), **ATT_TOL)
+
+
+# ------------------------------------------------------------------------------------------------ decode GEMV
+@pytest.mark.parametrize("n,k", [(4608, 3584), (3584, 3584), (3584, 18944), (1536, 512), (512, 1024), (37, 64)])
+def test_gemv_plain_and_residual(abi, n, k):
+    g = torch.Generator().manual_seed(n + k)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    x = torch.randn(k, generator=g).to(torch.bfloat16)
+    b = (torch.randn(n, generator=g) * 0.1).to(torch.bfloat16)
+    res = torch.randn(n, generator=g).to(torch.bfloat16)
+    nw = (1 + 0.1 * torch.randn(k, generator=g)).to(torch.bfloat16)
+    wd, xd = w.to(DEV), x.to(DEV)
+    y = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_bf16(wd, xd, y, 0, bias=b.to(DEV))
+    ref = torch.nn.functional.linear(x.float(), w.float(), b.float()).to(torch.bfloat16)
+    torch.testing.assert_close(y.cpu().float(), ref.float(), rtol=1.6e-2, atol=1e-2)
+    # RMSNorm prologue + residual epilogue, in place on the residual
+    yr = res.to(DEV).clone()
+    abi.gemv_bf16(wd, xd, yr, 1, norm_weight=nw.to(DEV), eps=1e-6, residual=yr)
+    xn = o_vit.rmsnorm(x[None], nw, 1e-6)[0]
+    ref = (res.float() + torch.nn.functional.linear(xn.float(), w.float()).to(torch.bfloat16).float()).to(torch.bfloat16)
+    torch.testing.assert_close(yr.cpu().float(), ref.float(), rtol=1.6e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,k", [(18944, 3584), (1024, 512), (100, 64)])
+def test_gemv_swiglu(abi, n, k):
+    g = torch.Generator().manual_seed(n)
+    w = (torch.randn(2 * n, k, generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    x = torch.randn(k, generator=g).to(torch.bfloat16)
+    nw = (1 + 0.1 * torch.randn(k, generator=g)).to(torch.bfloat16)
+    y = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_bf16(w.to(DEV), x.to(DEV), y, 2, norm_weight=nw.to(DEV), eps=1e-6)
+    xn = o_vit.rmsnorm(x[None], nw, 1e-6)[0]
+    gu = torch.nn.functional.linear(xn, w)
+    ref = torch.nn.functional.silu(gu[:n]) * gu[n:]
+    torch.testing.assert_close(y.cpu().float(), ref.float(), rtol=2e-2, atol=1e-2)
+
+
+def test_lm_head_argmax(abi):
+    g = torch.Generator().manual_seed(0)
+    n, k = 152064, 3584
+    w = (torch.randn(n, k, generator=g) * 0.02).to(torch.bfloat16)
+    nw = (1 + 0.1 * torch.randn(k, generator=g)).to(torch.bfloat16)
+    sup = torch.zeros(n, dtype=torch.uint8)
+    sup[151643:] = 1
+    key = torch.zeros(1, dtype=torch.int64, device=DEV)
+    tok = torch.zeros(1, dtype=torch.int64, device=DEV)
+    cnt = torch.tensor([100, 0, 7], dtype=torch.int32, device=DEV)
+    wd, nwd, supd = w.to(DEV), nw.to(DEV), sup.to(DEV)
+    for trial in range(4):
+        x = torch.randn(k, generator=g).to(torch.bfloat16)
+        abi.lm_head_argmax(wd, x.to(DEV), nwd, 1e-6, supd, key, tok, cnt[0:1], cnt[1:2], cnt[2:3])
+        xn = o_vit.rmsnorm(x[None], nw, 1e-6)[0]
+        logits = torch.nn.functional.linear(xn.float(), w.float()).to(torch.bfloat16).float()
+        logits[151643:] = -float("inf")
+        t = int(tok.item())
+        # the same bf16 logit value as the reference's maximum (ties and 1-ulp accumulation differences allowed)
+        assert logits[t] >= logits.max() - 0.016 * abs(float(logits.max())), (t, int(logits.argmax()))
+        assert t < 151643
+    assert cnt.tolist() == [104, 105, 11] and key.item() == 0
