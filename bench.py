@@ -248,6 +248,28 @@ def kernel_rooflines(engine, pk):
     t = timed(lambda: [_abi.gemm_bf16(a, engine.merger["w0"], engine.merger["b0"], y, 1) for _ in range(8)]) / 8
     out["patch_merger_gemm0"] = {"bound": "tensor", "achieved": 2.0 * 256 * 5120 * 5120 / t / 1e12, "peak": pk["bf16_burst"],
                                  "unit": "TFLOP/s", "us_per_launch": t * 1e6, "launches_per_step": 1}
+    # decode GEMVs (weight streaming, one launch per projection per layer; 28 layers = 13 GB >> L2)
+    x = torch.randn(g.hidden, device=dev).to(torch.bfloat16)
+    xr = torch.randn(g.hidden, device=dev).to(torch.bfloat16)
+    qkv_o = torch.empty((hq + 2 * g.num_kv_heads) * d, dtype=torch.bfloat16, device=dev)
+    att = torch.randn(hq * d, device=dev).to(torch.bfloat16)
+    act = torch.empty(g.mlp, dtype=torch.bfloat16, device=dev)
+    for name, fn, nbytes in [
+        ("gemv_norm_qkv", lambda Lw: _abi.gemv_bf16(Lw["wqkv"], x, qkv_o, 0, Lw["ln1"], g.rms_eps, Lw["bqkv"]), engine.layers[0]["wqkv"].numel() * 2),
+        ("gemv_o_residual", lambda Lw: _abi.gemv_bf16(Lw["wo"], att, xr, 1, residual=xr), engine.layers[0]["wo"].numel() * 2),
+        ("gemv_norm_gate_up_swiglu", lambda Lw: _abi.gemv_bf16(Lw["wgu"], x, act, 2, Lw["ln2"], g.rms_eps), engine.layers[0]["wgu"].numel() * 2),
+        ("gemv_down_residual", lambda Lw: _abi.gemv_bf16(Lw["wd"], act, xr, 1, residual=xr), engine.layers[0]["wd"].numel() * 2),
+    ]:
+        t = timed(lambda: [fn(Lw) for Lw in engine.layers]) / L
+        out[name] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "us_per_launch": t * 1e6,
+                     "launches_per_step": L * (NEW_TOKENS - 1), "weight_bytes": nbytes}
+    key = torch.zeros(1, dtype=torch.int64, device=dev)
+    tok = torch.zeros(1, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(3, dtype=torch.int32, device=dev)
+    t = timed(lambda: [_abi.lm_head_argmax(engine.lm_head, x, engine.norm, g.rms_eps, engine.suppress_u8, key, tok, cnt[0:1], cnt[1:2], cnt[2:3])
+                       for _ in range(4)]) / 4
+    out["gemv_norm_lm_head_argmax"] = {"bound": "hbm", "achieved": engine.lm_head.numel() * 2 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                       "us_per_launch": t * 1e6, "launches_per_step": NEW_TOKENS - 1, "weight_bytes": engine.lm_head.numel() * 2}
     for k, v in out.items():
         v["frac"] = v["achieved"] / v["peak"]
         v["traffic"] = None

@@ -44,121 +44,137 @@ __device__ __forceinline__ uint32_t ordered_f32(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-template <int MODE, int RW>
+// RG  = output rows per warp group (SWIGLU: RG gate rows + their RG up rows)
+// KS  = warps that split K for one row group (8 / KS row groups per CTA); partials are merged through shared memory
+// U   = k-steps (256 elements) whose loads are issued before the first FMA
+template <int MODE, int RG, int KS, int U, bool STAGE>
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) {
     extern __shared__ __align__(16) uint8_t gsm[];
     uint16_t* xs = reinterpret_cast<uint16_t*>(gsm);
+    constexpr int NR = (MODE == GEMV_SWIGLU) ? 2 * RG : RG;
+    constexpr int GROUPS = 8 / KS;
     __shared__ float red[8];
-    __shared__ unsigned long long best[8];
+    __shared__ float part[8][NR];
+    __shared__ unsigned long long best[GROUPS * RG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = p.K;
 
-    // ---- prologue: stage x (optionally RMS-normalised) in shared memory
-    float ss = 0.f;
-    for (int k = threadIdx.x * 8; k < K; k += GEMV_THREADS * 8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(p.x + k);
-        *reinterpret_cast<uint4*>(xs + k) = v;
-        if (p.norm_w) {
-            const uint32_t* q = &v.x;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float a = bf16_lo(q[i]), b = bf16_hi(q[i]); ss += a * a + b * b; }
-        }
-    }
-    if (p.norm_w) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-        if (lane == 0) red[warp] = ss;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tot += red[i];
-        const float r = rsqrtf(tot / (float)K + p.eps);
+    // ---- prologue: stage x (RMS-normalised when norm_w is given) in shared memory; plain/residual GEMVs without a
+    // norm read x straight from global memory (L1-resident after the first warp) and need no block barrier here
+    if (STAGE) {
+        float ss = 0.f;
         for (int k = threadIdx.x * 8; k < K; k += GEMV_THREADS * 8) {
-            uint4 v = *reinterpret_cast<uint4*>(xs + k);
-            const uint4 wv = *reinterpret_cast<const uint4*>(p.norm_w + k);
-            uint32_t* q = &v.x;
-            const uint32_t* wq = &wv.x;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                q[i] = pack_bf16(bf16_lo(wq[i]) * round_bf16(bf16_lo(q[i]) * r), bf16_hi(wq[i]) * round_bf16(bf16_hi(q[i]) * r));
+            const uint4 v = *reinterpret_cast<const uint4*>(p.x + k);
             *reinterpret_cast<uint4*>(xs + k) = v;
+            if (p.norm_w) {
+                const uint32_t* q = &v.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float a = bf16_lo(q[i]), b = bf16_hi(q[i]); ss += a * a + b * b; }
+            }
         }
+        if (p.norm_w) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+            if (lane == 0) red[warp] = ss;
+            __syncthreads();
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += red[i];
+            const float r = rsqrtf(tot / (float)K + p.eps);
+            for (int k = threadIdx.x * 8; k < K; k += GEMV_THREADS * 8) {
+                uint4 v = *reinterpret_cast<uint4*>(xs + k);
+                const uint4 wv = *reinterpret_cast<const uint4*>(p.norm_w + k);
+                uint32_t* q = &v.x;
+                const uint32_t* wq = &wv.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    q[i] = pack_bf16(bf16_lo(wq[i]) * round_bf16(bf16_lo(q[i]) * r), bf16_hi(wq[i]) * round_bf16(bf16_hi(q[i]) * r));
+                *reinterpret_cast<uint4*>(xs + k) = v;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- body: RW rows per warp (SWIGLU: RW gate rows + their RW up rows)
-    constexpr int NR = (MODE == GEMV_SWIGLU) ? 2 * RW : RW;
-    const int n0 = (blockIdx.x * 8 + warp) * RW;
+    // ---- body
+    const int grp = warp / KS, ks = warp % KS;
+    const int n0 = (blockIdx.x * GROUPS + grp) * RG;
     const uint16_t* rows[NR];
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
+    for (int r = 0; r < RG; ++r) {
         const int n = min(n0 + r, p.N - 1);
         rows[r] = p.W + (int64_t)n * K;
-        if (MODE == GEMV_SWIGLU) rows[RW + r] = p.W + (int64_t)(p.N + n) * K;
+        if (MODE == GEMV_SWIGLU) rows[RG + r] = p.W + (int64_t)(p.N + n) * K;
     }
     float acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.f;
-    int k = lane * 8;
-    for (; k + 256 < K; k += 512) {
-        uint4 w0[NR], w1[NR];
+    const int steps = (K + 255) >> 8;
+    const int s_begin = steps * ks / KS, s_end = steps * (ks + 1) / KS;
+    for (int s0 = s_begin; s0 < s_end; s0 += U) {
+        uint4 w[U][NR], xv[U];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) { w0[r] = ld_nc_v4(rows[r] + k); w1[r] = ld_nc_v4(rows[r] + k + 256); }
-        const uint4 x0 = *reinterpret_cast<const uint4*>(xs + k);
-        const uint4 x1 = *reinterpret_cast<const uint4*>(xs + k + 256);
+        for (int u = 0; u < U; ++u) {
+            const int k = ((s0 + u) << 8) + lane * 8;
+            const bool ok = (s0 + u < s_end) && (k < K);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += dot8(w0[r], x0) + dot8(w1[r], x1);
-    }
-    for (; k < K; k += 256) {
-        const uint4 x0 = *reinterpret_cast<const uint4*>(xs + k);
+            for (int r = 0; r < NR; ++r) w[u][r] = ok ? ld_nc_v4(rows[r] + k) : make_uint4(0, 0, 0, 0);
+            xv[u] = ok ? (STAGE ? *reinterpret_cast<const uint4*>(xs + k) : __ldg(reinterpret_cast<const uint4*>(p.x + k)))
+                       : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += dot8(ld_nc_v4(rows[r] + k), x0);
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] += dot8(w[u][r], xv[u]);
+        }
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], d);
     }
-
-    // ---- epilogue
-    if (MODE == GEMV_ARGMAX) {
-        unsigned long long mine = 0ull;
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < RW; ++r) {
-                const int n = n0 + r;
-                if (n < p.N && !(p.suppress && p.suppress[n])) {
-                    const float logit = round_bf16(acc[r]);
-                    const unsigned long long key = ((unsigned long long)ordered_f32(logit) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
-                    mine = key > mine ? key : mine;
-                }
-            }
-            best[warp] = mine;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long b = 0ull;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b = best[i] > b ? best[i] : b;
-            if (b) atomicMax(p.key, b);
-        }
-        return;
-    }
     if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            const int n = n0 + r;
-            if (n >= p.N) break;
-            if (MODE == GEMV_SWIGLU) {
-                const float g = round_bf16(acc[r]), u = round_bf16(acc[RW + r]);
-                const float s = round_bf16(g / (1.0f + __expf(-g)));
-                p.y[n] = __bfloat16_as_ushort(__float2bfloat16_rn(s * u));
+        for (int r = 0; r < NR; ++r) part[warp][r] = acc[r];
+    }
+    __syncthreads();
+
+    // ---- epilogue: thread t finishes output row (group t / RG, row t % RG)
+    const int t = threadIdx.x;
+    unsigned long long mine = 0ull;
+    if (t < GROUPS * RG) {
+        const int g = t / RG, r = t % RG;
+        const int n = (blockIdx.x * GROUPS + g) * RG + r;
+        float v = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int k2 = 0; k2 < KS; ++k2) {
+            v += part[g * KS + k2][r];
+            if (MODE == GEMV_SWIGLU) v2 += part[g * KS + k2][RG + r];
+        }
+        if (n < p.N) {
+            if (MODE == GEMV_ARGMAX) {
+                if (!(p.suppress && p.suppress[n])) {
+                    const float logit = round_bf16(v);
+                    mine = ((unsigned long long)ordered_f32(logit) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                }
+            } else if (MODE == GEMV_SWIGLU) {
+                const float gt = round_bf16(v), up = round_bf16(v2);
+                const float sl = round_bf16(gt / (1.0f + __expf(-gt)));
+                p.y[n] = __bfloat16_as_ushort(__float2bfloat16_rn(sl * up));
             } else {
-                float v = acc[r];
                 if (p.bias) v += __bfloat162float(__ushort_as_bfloat16(p.bias[n]));
                 if (MODE == GEMV_RESID) v = round_bf16(v) + __bfloat162float(__ushort_as_bfloat16(p.residual[n]));
                 p.y[n] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
             }
+        }
+    }
+    if (MODE == GEMV_ARGMAX) {
+        if (t < GROUPS * RG) best[t] = mine;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long bb = 0ull;
+#pragma unroll
+            for (int i = 0; i < GROUPS * RG; ++i) bb = best[i] > bb ? best[i] : bb;
+            if (bb) atomicMax(p.key, bb);
         }
     }
 }
@@ -174,29 +190,40 @@ __global__ void decode_finalize_kernel(unsigned long long* key, int64_t* tok, in
     *next_pos = *next_pos + 1;
 }
 
-template <int MODE, int RW>
+template <int MODE, int RG, int KS, int U, bool STAGE>
 static int launch_gemv(const GemvParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)p.K * 2;
+    const size_t smem = STAGE ? (size_t)p.K * 2 : 0;
     static bool attr_done = false;
     if (!attr_done && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<MODE, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<MODE, RG, KS, U, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemv_kernel) failed: %s", cudaGetErrorString(e));
             return SVLM_ECUDA;
         }
         attr_done = true;
     }
-    const int grid = (p.N + 8 * RW - 1) / (8 * RW);
-    gemv_kernel<MODE, RW><<<grid, GEMV_THREADS, smem, st>>>(p);
+    const int rows_per_cta = (8 / KS) * RG;
+    const int grid = (p.N + rows_per_cta - 1) / rows_per_cta;
+    gemv_kernel<MODE, RG, KS, U, STAGE><<<grid, GEMV_THREADS, smem, st>>>(p);
     return launch_status("gemv_kernel");
+}
+
+// Shape heuristics (B200, 148 SMs): enough CTAs x bytes in flight to cover the HBM latency-bandwidth product.
+//   long rows (K >= 8192, the MLP down projection): 8 warps split K for 4 rows
+//   few rows  (N < 16384: q/k/v, o):                2 warps split K for 2 rows, 4 k-steps in flight
+//   many rows (gate/up, lm_head):                   one warp owns its rows
+template <int MODE, bool STAGE>
+static int dispatch_shape(const GemvParams& p, cudaStream_t st) {
+    if (MODE == GEMV_SWIGLU) return launch_gemv<MODE, 2, 1, 2, STAGE>(p, st);
+    if (MODE == GEMV_ARGMAX) return launch_gemv<MODE, 4, 1, 2, STAGE>(p, st);
+    if (p.K >= 8192) return launch_gemv<MODE, 4, 8, 2, STAGE>(p, st);
+    if (p.N < 16384) return launch_gemv<MODE, 2, 2, 4, STAGE>(p, st);
+    return launch_gemv<MODE, 4, 1, 2, STAGE>(p, st);
 }
 
 template <int MODE>
 static int dispatch_rw(const GemvParams& p, cudaStream_t st) {
-    // 4 rows per warp once that still gives every SM >= 2 CTAs; otherwise 2 (more CTAs for the small projections)
-    const int rows_total = p.N;
-    if (MODE != GEMV_SWIGLU && rows_total / 32 >= 2 * 148) return launch_gemv<MODE, 4>(p, st);
-    return launch_gemv<MODE, 2>(p, st);
+    return p.norm_w ? dispatch_shape<MODE, true>(p, st) : dispatch_shape<MODE, false>(p, st);
 }
 
 }  // namespace svlm
