@@ -371,8 +371,13 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
     float acc = 0.f;
     const float* src = part_o + (int64_t)r * D + d;
     const int64_t stride = (int64_t)rows * D;
-#pragma unroll 8
-    for (int s = 0; s < num_splits; ++s) acc += w_s[s] * src[s * stride];
+    for (int s0 = 0; s0 < num_splits; s0 += 16) {       // 16 independent loads in flight per thread
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = (s0 + u < num_splits) ? __ldcg(src + (s0 + u) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += (s0 + u < num_splits ? w_s[s0 + u] : 0.f) * v[u];
+    }
     out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
 }
 
