@@ -16,9 +16,9 @@ import torch
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libsvlm_b200.so")
-SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "gemm.cu", "gemv.cu"]
+SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "attn_decode.cu", "gemm.cu", "gemv.cu"]
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "svlm_b200.h")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-rdc=false",
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
@@ -37,7 +37,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.join(_CSRC, "common.cuh"), HEADER]
+    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "attn_common.cuh"), HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

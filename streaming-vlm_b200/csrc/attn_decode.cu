@@ -1,0 +1,341 @@
+// Split-KV decode attention (Tq = 1) for sm_100a on tcgen05 / TMEM / TMA, "swap-AB" formulation.
+//
+// With one query token only G (= q heads per kv head, 7 for the 7B geometry) of the 128 rows of a Q tile would be
+// real, and a row-per-thread softmax would leave 121 of 128 threads idle while 7 threads walk 128 scores each.
+// Here the KEYS are the M dimension instead:
+//     S^T[128 keys x 16] = K_tile[128 x D] (A, K-major smem)  x  Q^T (B = Q [16 heads x D], K-major smem)
+//     O^T[D=128 x 16]   += V_tile^T (A = V tile [128 keys x D] read MN-major) x P^T (B = P [16 heads x 128 keys], K-major smem)
+// so every one of the 128 softmax threads owns ONE key and G scores (tcgen05.ld 32x32b.x16), the UMMAs are
+// M128 N16 (8 + 8 tiny instructions per tile), and the kernel is limited by the TMA stream of K/V tiles, i.e. HBM.
+// The per-head running maximum is shared by all keys of a tile (the accumulator rows are head-dim lanes), so the
+// tile maximum is reduced across the 128 threads (shuffles + one named barrier); the row sums stay per-thread until
+// the end.  Partial (m, l, O) per split go to the fp32 workspace and are merged by attn_combine_kernel.
+//
+// CTA = 192 threads (warp 0 TMA producer, warp 1 UMMA issuer, warps 2-5 softmax/epilogue), grid = (splits, H_kv).
+#include <math.h>
+
+#include "attn_common.cuh"
+
+namespace svlm {
+
+constexpr int DEC_BN = 128;
+constexpr int DEC_STAGES = 3;
+constexpr int DEC_PANEL = 128 * 128;           // 128 keys x 64 dims
+constexpr int DEC_TILE = 2 * DEC_PANEL;        // 128 keys x 128 dims
+constexpr int DEC_QP_PANEL = 16 * 128;         // 16 rows x 64 elements (Q and P^T operands)
+constexpr int DEC_THREADS = 192;
+constexpr int DEC_SMEM = 1024 + 2 * DEC_STAGES * DEC_TILE + 2 * DEC_QP_PANEL + 2 * 2 * DEC_QP_PANEL + 1024;
+
+struct DecParams {
+    int Hq, G, D;
+    int kv_len;
+    const int32_t* kv_len_dev;
+    int num_splits;
+    int kv_head_base;
+    uint16_t* out;        // bf16 [Hq][D]           (num_splits == 1)
+    float* part_o;        // fp32 [splits][Hq][D]
+    float2* part_ml;      // (m, l) [splits][Hq]
+    float scale_log2;
+};
+
+struct DecShared {
+    uint64_t q_full;
+    uint64_t k_full[DEC_STAGES], k_empty[DEC_STAGES];
+    uint64_t v_full[DEC_STAGES], v_empty[DEC_STAGES];
+    uint64_t s_full[2], p_full[2];
+    uint64_t o_done[2];
+    uint32_t tmem_base;
+    float wmax[2][4][16];      // [tile parity][softmax warp][head]
+    float lsum[4][16];
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const DecParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + DEC_STAGES * DEC_TILE;
+    uint8_t* sQ = sV + DEC_STAGES * DEC_TILE;            // 2 panels of [16 heads][64 dims]
+    uint8_t* sP = sQ + 2 * DEC_QP_PANEL;                 // 2 buffers x 2 panels of [16 heads][64 keys]
+    DecShared* sh = reinterpret_cast<DecShared*>(sP + 2 * 2 * DEC_QP_PANEL);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, head = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(&sh->q_full, 1);
+        for (int s = 0; s < DEC_STAGES; ++s) {
+            mbar_init(&sh->k_full[s], 1); mbar_init(&sh->k_empty[s], 1);
+            mbar_init(&sh->v_full[s], 1); mbar_init(&sh->v_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh->s_full[b], 1); mbar_init(&sh->p_full[b], 128); mbar_init(&sh->o_done[b], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<64>(&sh->tmem_base);
+    // P^T rows that no thread writes (heads >= G) must be zero, not stale shared memory
+    for (int i = threadIdx.x; i < 2 * 2 * DEC_QP_PANEL / 16; i += DEC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sh->tmem_base;
+
+    const int kv_len = p.kv_len_dev ? __ldg(p.kv_len_dev) : p.kv_len;
+    const int n_total = (kv_len + DEC_BN - 1) / DEC_BN;
+    const int tps = (n_total + p.num_splits - 1) / p.num_splits;
+    const int my_begin = split * tps;
+    const int n_tiles = max(min(n_total, my_begin + tps) - my_begin, 0);
+    const int kv_coord = p.kv_head_base + head;
+    const int G = p.G;
+
+    constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 16, 0, 0);   // A = K tile (K-major), B = Q (K-major)
+    constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 16, 1, 0);   // A = V tile read MN-major, B = P^T (K-major)
+
+    if (warp == 0) {
+        if (lane == 0 && n_tiles > 0) {
+            mbar_arrive_expect_tx(&sh->q_full, 2 * DEC_QP_PANEL);
+            tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, 0);
+            tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % DEC_STAGES;
+                const uint32_t ph = (j / DEC_STAGES) & 1;
+                const int row = (my_begin + j) * DEC_BN;
+                mbar_wait(&sh->k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&sh->k_full[s], DEC_TILE);
+                tma_load_3d(sK + s * DEC_TILE, &tmK, &sh->k_full[s], 0, row, kv_coord);
+                tma_load_3d(sK + s * DEC_TILE + DEC_PANEL, &tmK, &sh->k_full[s], 64, row, kv_coord);
+                mbar_wait(&sh->v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&sh->v_full[s], DEC_TILE);
+                tma_load_3d(sV + s * DEC_TILE, &tmV, &sh->v_full[s], 0, row, kv_coord);
+                tma_load_3d(sV + s * DEC_TILE + DEC_PANEL, &tmV, &sh->v_full[s], 64, row, kv_coord);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t q_addr = smem_u32(sQ);
+            auto issue_s = [&](int stage, int buf) {
+                const uint32_t k_addr = smem_u32(sK + stage * DEC_TILE);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t ka = k_addr + (uint32_t)(kk >> 2) * DEC_PANEL + (uint32_t)(kk & 3) * 32u;
+                    const uint32_t qa = q_addr + (uint32_t)(kk >> 2) * DEC_QP_PANEL + (uint32_t)(kk & 3) * 32u;
+                    umma_ss(tmem + buf * 16, umma_desc_sw128(ka, 16, 1024), umma_desc_sw128(qa, 16, 1024), IDESC_S, kk > 0 ? 1u : 0u);
+                }
+            };
+            auto issue_o = [&](int stage, int buf, bool acc) {
+                const uint32_t v_addr = smem_u32(sV + stage * DEC_TILE);
+                const uint32_t p_addr = smem_u32(sP + buf * 2 * DEC_QP_PANEL);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    // A: 16 keys (rows of 128 B) per step, the two 64-dim panels DEC_PANEL apart (MN-major, LBO = panel stride)
+                    const uint32_t pa = p_addr + (uint32_t)(kk >> 2) * DEC_QP_PANEL + (uint32_t)(kk & 3) * 32u;
+                    umma_ss(tmem + 32, umma_desc_sw128(v_addr + kk * 2048, DEC_PANEL, 1024), umma_desc_sw128(pa, 16, 1024), IDESC_O,
+                            (acc || kk > 0) ? 1u : 0u);
+                }
+            };
+            mbar_wait(&sh->q_full, 0);
+            mbar_wait(&sh->k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            umma_commit(&sh->k_empty[0]);
+            umma_commit(&sh->s_full[0]);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) {
+                    const int s1 = (j + 1) % DEC_STAGES;
+                    mbar_wait(&sh->k_full[s1], ((j + 1) / DEC_STAGES) & 1);
+                    tc_fence_after();
+                    issue_s(s1, (j + 1) & 1);
+                    umma_commit(&sh->k_empty[s1]);
+                    umma_commit(&sh->s_full[(j + 1) & 1]);
+                }
+                const int s = j % DEC_STAGES;
+                mbar_wait(&sh->p_full[j & 1], (j >> 1) & 1);
+                mbar_wait(&sh->v_full[s], (j / DEC_STAGES) & 1);
+                tc_fence_after();
+                issue_o(s, j & 1, j > 0);
+                umma_commit(&sh->v_empty[s]);
+                umma_commit(&sh->o_done[j & 1]);
+            }
+        }
+    } else {
+        // ---- softmax: thread = one key of the tile; epilogue: thread = one head-dim lane of O^T
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        float m_run[16], l_thr[16];
+#pragma unroll
+        for (int h = 0; h < 16; ++h) { m_run[h] = -INFINITY; l_thr[h] = 0.f; }
+        // byte offset of this key inside a P^T panel row (128B swizzle: 16-byte chunk index XOR (row & 7))
+        const int kcol = row & 63;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int b = j & 1;
+            const int key = (my_begin + j) * DEC_BN + row;
+            mbar_wait(&sh->s_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sr[16];
+            tmem_ld16(tmem + lane_addr + b * 16, sr);
+            tmem_wait_ld();
+            float sc[16];
+            const bool live = key < kv_len;
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+                sc[h] = (live && h < G) ? __uint_as_float(sr[h]) * p.scale_log2 : -INFINITY;
+                if (h < G) {                         // G is CTA-uniform: heads >= G skip the reduction
+                    float mx = sc[h];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (lane == h) sh->wmax[b][q4][h] = mx;
+                }
+            }
+            named_bar_sync(1, 128);
+            bool any_upd = false;
+            float alpha[16];
+            uint32_t pk[16];
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+                const float mt = (h < G) ? fmaxf(fmaxf(sh->wmax[b][0][h], sh->wmax[b][1][h]), fmaxf(sh->wmax[b][2][h], sh->wmax[b][3][h]))
+                                         : -INFINITY;
+                const bool upd = mt > m_run[h];
+                const float m_new = upd ? mt : m_run[h];
+                alpha[h] = upd ? ex2_approx(m_run[h] - m_new) : 1.0f;     // -inf -> 0 on the first tile
+                any_upd |= (upd && h < G);
+                m_run[h] = m_new;
+                const float pv = (h < G) ? ex2_approx(sc[h] - m_new) : 0.f;  // m_new finite for h < G (tile has >= 1 live key)
+                l_thr[h] = l_thr[h] * alpha[h] + pv;
+                pk[h] = __float_as_uint(pv);
+            }
+            if (any_upd && j > 0) {
+                // rescale O^T (head-dim lane x head column); PV(j-1) must have landed (see attn_fwd.cu for the parity argument)
+                mbar_wait(&sh->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                uint32_t orow[16];
+                tmem_ld16(tmem + lane_addr + 32, orow);
+                tmem_wait_ld();
+#pragma unroll
+                for (int h = 0; h < 16; ++h) orow[h] = __float_as_uint(__uint_as_float(orow[h]) * alpha[h]);
+                tmem_st16(tmem + lane_addr + 32, orow);
+                tmem_wait_st();
+            }
+            // P^T[h][key] -> shared memory operand (K-major, 128B swizzle), rows >= G stay zero
+            uint8_t* pb = sP + b * 2 * DEC_QP_PANEL + (row >> 6) * DEC_QP_PANEL;
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+                if (h < G) {
+                    const uint32_t off = (uint32_t)h * 128u + ((((uint32_t)kcol >> 3) ^ ((uint32_t)h & 7u)) << 4) + ((uint32_t)kcol & 7u) * 2u;
+                    *reinterpret_cast<uint16_t*>(pb + off) = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(pk[h])));
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&sh->p_full[b]);
+        }
+
+        // ---- epilogue: total row sums (one reduction), then O^T lanes
+        float l_tot[16];
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            float v = l_thr[h];
+            if (h < G) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            }
+            if (lane == h) sh->lsum[q4][h] = v;
+        }
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 16; ++h) l_tot[h] = sh->lsum[0][h] + sh->lsum[1][h] + sh->lsum[2][h] + sh->lsum[3][h];
+        uint32_t orow[16];
+        if (n_tiles > 0) {
+            mbar_wait(&sh->o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+            tc_fence_after();
+            tmem_ld16(tmem + lane_addr + 32, orow);
+            tmem_wait_ld();
+        } else {
+#pragma unroll
+            for (int h = 0; h < 16; ++h) orow[h] = 0u;
+        }
+        const int d = row;                         // O^T lane = head-dim index
+        if (d < p.D) {
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+                if (h >= G) break;
+                const int hq = head * G + h;
+                if (p.num_splits == 1) {
+                    const float inv = l_tot[h] > 0.f ? 1.0f / l_tot[h] : 0.f;
+                    p.out[(int64_t)hq * p.D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(orow[h]) * inv));
+                } else {
+                    p.part_o[((int64_t)split * p.Hq + hq) * p.D + d] = __uint_as_float(orow[h]);
+                }
+            }
+        }
+        if (p.num_splits > 1) {
+#pragma unroll
+            for (int h = 0; h < 16; ++h)
+                if (row == h && h < G) p.part_ml[(int64_t)split * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<64>(tmem);
+}
+
+int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
+                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st) {
+    const int D = arena->head_dim, H = arena->kv_heads, G = q_heads / H;
+    ArenaDims ad{arena->layers, H, D, arena->capacity};
+    const uint16_t* base = (const uint16_t*)arena->base;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    {
+        uint64_t dims[3] = {(uint64_t)D, (uint64_t)q_heads, 1};
+        uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)q_heads * D * 2};
+        uint32_t box[3] = {64, 16, 1};
+        if ((rc = make_tensor_map_bf16(&tq, q, 3, dims, str, box, 1))) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)D, (uint64_t)ad.cap, (uint64_t)ad.L * H};
+        uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)ad.cap * D * 2};
+        uint32_t box[3] = {64, DEC_BN, 1};
+        if ((rc = make_tensor_map_bf16(&tk, base + ad.offset(buffer, SVLM_PLANE_K_ROT, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&tv, base + ad.offset(buffer, SVLM_PLANE_V, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+    }
+    DecParams p{};
+    p.Hq = q_heads; p.G = G; p.D = D;
+    p.kv_len = kv_len; p.kv_len_dev = kv_len_dev; p.num_splits = num_splits;
+    p.kv_head_base = layer * H;
+    p.out = (uint16_t*)out;
+    p.part_o = (float*)workspace;
+    p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + (size_t)num_splits * q_heads * D) : nullptr;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", DEC_SMEM, cudaGetErrorString(e));
+            return SVLM_ECUDA;
+        }
+        attr_done = true;
+    }
+    attn_decode_kernel<<<dim3(num_splits, H), DEC_THREADS, DEC_SMEM, st>>>(tq, tk, tv, p);
+    if ((rc = launch_status("attn_decode_kernel"))) return rc;
+    if (num_splits > 1) {
+        attn_combine_kernel<<<q_heads, 128, 0, st>>>(p.part_o, p.part_ml, p.out, q_heads, D, num_splits);
+        return launch_status("attn_combine_kernel");
+    }
+    return SVLM_OK;
+}
+
+}  // namespace svlm

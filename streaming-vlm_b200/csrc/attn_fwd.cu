@@ -18,7 +18,7 @@
 // TMEM: S0 [0,128) | S1 [128,256) | O [256,384) columns, fp32, 128 lanes.
 #include <math.h>
 
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace svlm {
 
@@ -429,6 +429,8 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
     SVLM_REQUIRE(G <= 128, "group size %d too large", G);
     const size_t need = svlm_attn_workspace_bytes(n_q_tokens, q_heads, D, num_splits);
     SVLM_REQUIRE(num_splits == 1 || (workspace != nullptr && workspace_bytes >= need), "workspace too small: need %zu bytes", need);
+    if (n_q_tokens == 1 && G <= 16)   // decode: swap-AB kernel (attn_decode.cu)
+        return attn_decode_launch(arena, buffer, layer, q, out, q_heads, kv_len, kv_len_dev, num_splits, workspace, scale, (cudaStream_t)stream);
 
     ArenaDims ad{arena->layers, H, D, arena->capacity};
     const uint16_t* base = (const uint16_t*)arena->base;
