@@ -36,7 +36,14 @@ struct DecParams {
     float* part_o;        // fp32 [splits][Hq][D]
     float2* part_ml;      // (m, l) [splits][Hq]
     float scale_log2;
+    unsigned long long* trace;   // SVLM_TRACE builds only: [cta][tile][8] clock64 stamps
 };
+
+#ifdef SVLM_TRACE
+#define TRACE(ev, tile) do { if (p.trace && (tile) < 32) p.trace[((blockIdx.y * gridDim.x + blockIdx.x) * 32 + (tile)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(ev, tile) do { } while (0)
+#endif
 
 struct DecShared {
     uint64_t q_full;
@@ -45,20 +52,31 @@ struct DecShared {
     uint64_t s_full[2], p_full[2];
     uint64_t o_done[2];
     uint32_t tmem_base;
-    float wmax[2][4][16];      // [tile parity][softmax warp][head]
-    float lsum[4][16];
+    float wmax[2][4][8];       // [tile parity][softmax warp][head]
+    float lsum[4][8];
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+__device__ __forceinline__ int ordered_i32(float f) {            // monotonic float -> int map (for redux.sync.max.s32)
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float unordered_f32(int i) { return __int_as_float(i >= 0 ? i : (i ^ 0x7fffffff)); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 
+template <int G>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const DecParams p) {
@@ -98,32 +116,45 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int my_begin = split * tps;
     const int n_tiles = max(min(n_total, my_begin + tps) - my_begin, 0);
     const int kv_coord = p.kv_head_base + head;
-    const int G = p.G;
 
     constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 16, 0, 0);   // A = K tile (K-major), B = Q (K-major)
     constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 16, 1, 0);   // A = V tile read MN-major, B = P^T (K-major)
 
     if (warp == 0) {
-        if (lane == 0 && n_tiles > 0) {
-            mbar_arrive_expect_tx(&sh->q_full, 2 * DEC_QP_PANEL);
-            tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, 0);
-            tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, 0);
+        // TMA producer: uniform control flow for the whole warp, one elected lane issues (same reason as the UMMA warp)
+        if (n_tiles > 0) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&sh->q_full, 2 * DEC_QP_PANEL);
+                tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, 0);
+                tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, 0);
+            }
+            __syncwarp();
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % DEC_STAGES;
                 const uint32_t ph = (j / DEC_STAGES) & 1;
                 const int row = (my_begin + j) * DEC_BN;
                 mbar_wait(&sh->k_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&sh->k_full[s], DEC_TILE);
-                tma_load_3d(sK + s * DEC_TILE, &tmK, &sh->k_full[s], 0, row, kv_coord);
-                tma_load_3d(sK + s * DEC_TILE + DEC_PANEL, &tmK, &sh->k_full[s], 64, row, kv_coord);
+                TRACE(7, j);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&sh->k_full[s], DEC_TILE);
+                    tma_load_3d(sK + s * DEC_TILE, &tmK, &sh->k_full[s], 0, row, kv_coord);
+                    tma_load_3d(sK + s * DEC_TILE + DEC_PANEL, &tmK, &sh->k_full[s], 64, row, kv_coord);
+                }
+                __syncwarp();
                 mbar_wait(&sh->v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&sh->v_full[s], DEC_TILE);
-                tma_load_3d(sV + s * DEC_TILE, &tmV, &sh->v_full[s], 0, row, kv_coord);
-                tma_load_3d(sV + s * DEC_TILE + DEC_PANEL, &tmV, &sh->v_full[s], 64, row, kv_coord);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&sh->v_full[s], DEC_TILE);
+                    tma_load_3d(sV + s * DEC_TILE, &tmV, &sh->v_full[s], 0, row, kv_coord);
+                    tma_load_3d(sV + s * DEC_TILE + DEC_PANEL, &tmV, &sh->v_full[s], 64, row, kv_coord);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && n_tiles > 0) {
+        // UMMA issuer.  The whole warp walks the loop (uniform control flow and operands, so the descriptors live in
+        // uniform registers); one elected lane issues.  A divergent `if (lane == 0)` around the loop makes ptxas wrap every
+        // tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall (~100 cycles per instruction, measured).
+        if (n_tiles > 0) {
             const uint32_t q_addr = smem_u32(sQ);
             auto issue_s = [&](int stage, int buf) {
                 const uint32_t k_addr = smem_u32(sK + stage * DEC_TILE);
@@ -148,25 +179,34 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(&sh->q_full, 0);
             mbar_wait(&sh->k_full[0], 0);
             tc_fence_after();
-            issue_s(0, 0);
-            umma_commit(&sh->k_empty[0]);
-            umma_commit(&sh->s_full[0]);
+            if (elect_one()) {
+                issue_s(0, 0);
+                umma_commit(&sh->k_empty[0]);
+                umma_commit(&sh->s_full[0]);
+            }
+            __syncwarp();
             for (int j = 0; j < n_tiles; ++j) {
                 if (j + 1 < n_tiles) {
                     const int s1 = (j + 1) % DEC_STAGES;
                     mbar_wait(&sh->k_full[s1], ((j + 1) / DEC_STAGES) & 1);
                     tc_fence_after();
-                    issue_s(s1, (j + 1) & 1);
-                    umma_commit(&sh->k_empty[s1]);
-                    umma_commit(&sh->s_full[(j + 1) & 1]);
+                    if (elect_one()) {
+                        issue_s(s1, (j + 1) & 1);
+                        umma_commit(&sh->k_empty[s1]);
+                        umma_commit(&sh->s_full[(j + 1) & 1]);
+                    }
+                    __syncwarp();
                 }
                 const int s = j % DEC_STAGES;
                 mbar_wait(&sh->p_full[j & 1], (j >> 1) & 1);
                 mbar_wait(&sh->v_full[s], (j / DEC_STAGES) & 1);
                 tc_fence_after();
-                issue_o(s, j & 1, j > 0);
-                umma_commit(&sh->v_empty[s]);
-                umma_commit(&sh->o_done[j & 1]);
+                if (elect_one()) {
+                    issue_o(s, j & 1, j > 0);
+                    umma_commit(&sh->v_empty[s]);
+                    umma_commit(&sh->o_done[j & 1]);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -174,103 +214,98 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int q4 = warp & 3;
         const int row = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-        float m_run[16], l_thr[16];
+        float m_run[G], l_thr[G];
 #pragma unroll
-        for (int h = 0; h < 16; ++h) { m_run[h] = -INFINITY; l_thr[h] = 0.f; }
-        // byte offset of this key inside a P^T panel row (128B swizzle: 16-byte chunk index XOR (row & 7))
-        const int kcol = row & 63;
+        for (int h = 0; h < G; ++h) { m_run[h] = -INFINITY; l_thr[h] = 0.f; }
+        const int kcol = row & 63;                 // key column inside a 64-key P^T panel
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
             const int key = (my_begin + j) * DEC_BN + row;
+            if (row == 0) TRACE(0, j);
             mbar_wait(&sh->s_full[b], (j >> 1) & 1);
             tc_fence_after();
-            uint32_t sr[16];
-            tmem_ld16(tmem + lane_addr + b * 16, sr);
+            if (row == 0) TRACE(1, j);
+            uint32_t sr[8];
+            tmem_ld8(tmem + lane_addr + b * 16, sr);
             tmem_wait_ld();
-            float sc[16];
+            if (row == 0) TRACE(2, j);
             const bool live = key < kv_len;
+            float sc[G];
 #pragma unroll
-            for (int h = 0; h < 16; ++h) {
-                sc[h] = (live && h < G) ? __uint_as_float(sr[h]) * p.scale_log2 : -INFINITY;
-                if (h < G) {                         // G is CTA-uniform: heads >= G skip the reduction
-                    float mx = sc[h];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    if (lane == h) sh->wmax[b][q4][h] = mx;
-                }
+            for (int h = 0; h < G; ++h) {
+                sc[h] = live ? __uint_as_float(sr[h]) * p.scale_log2 : -INFINITY;
+                const int mx = __reduce_max_sync(0xffffffffu, ordered_i32(sc[h]));   // one REDUX per head
+                if (lane == h) sh->wmax[b][q4][h] = unordered_f32(mx);
             }
             named_bar_sync(1, 128);
+            if (row == 0) TRACE(3, j);
             bool any_upd = false;
-            float alpha[16];
-            uint32_t pk[16];
+            float alpha[G], pv[G];
 #pragma unroll
-            for (int h = 0; h < 16; ++h) {
-                const float mt = (h < G) ? fmaxf(fmaxf(sh->wmax[b][0][h], sh->wmax[b][1][h]), fmaxf(sh->wmax[b][2][h], sh->wmax[b][3][h]))
-                                         : -INFINITY;
+            for (int h = 0; h < G; ++h) {
+                const float mt = fmaxf(fmaxf(sh->wmax[b][0][h], sh->wmax[b][1][h]), fmaxf(sh->wmax[b][2][h], sh->wmax[b][3][h]));
                 const bool upd = mt > m_run[h];
-                const float m_new = upd ? mt : m_run[h];
+                const float m_new = upd ? mt : m_run[h];                  // finite: every tile has at least one live key
                 alpha[h] = upd ? ex2_approx(m_run[h] - m_new) : 1.0f;     // -inf -> 0 on the first tile
-                any_upd |= (upd && h < G);
+                any_upd |= upd;
                 m_run[h] = m_new;
-                const float pv = (h < G) ? ex2_approx(sc[h] - m_new) : 0.f;  // m_new finite for h < G (tile has >= 1 live key)
-                l_thr[h] = l_thr[h] * alpha[h] + pv;
-                pk[h] = __float_as_uint(pv);
+                pv[h] = ex2_approx(sc[h] - m_new);
+                l_thr[h] = l_thr[h] * alpha[h] + pv[h];
             }
+            if (row == 0) TRACE(5, j);
             if (any_upd && j > 0) {
                 // rescale O^T (head-dim lane x head column); PV(j-1) must have landed (see attn_fwd.cu for the parity argument)
                 mbar_wait(&sh->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                uint32_t orow[16];
-                tmem_ld16(tmem + lane_addr + 32, orow);
+                uint32_t orow[8];
+                tmem_ld8(tmem + lane_addr + 32, orow);
                 tmem_wait_ld();
 #pragma unroll
-                for (int h = 0; h < 16; ++h) orow[h] = __float_as_uint(__uint_as_float(orow[h]) * alpha[h]);
-                tmem_st16(tmem + lane_addr + 32, orow);
+                for (int h = 0; h < G; ++h) orow[h] = __float_as_uint(__uint_as_float(orow[h]) * alpha[h]);
+                tmem_st8(tmem + lane_addr + 32, orow);
                 tmem_wait_st();
             }
-            // P^T[h][key] -> shared memory operand (K-major, 128B swizzle), rows >= G stay zero
+            if (row == 0) TRACE(6, j);
+            // P^T[h][key] -> shared memory operand (K-major, 128B swizzle: 16-byte chunk index XOR (h & 7)); rows >= G stay zero
             uint8_t* pb = sP + b * 2 * DEC_QP_PANEL + (row >> 6) * DEC_QP_PANEL;
 #pragma unroll
-            for (int h = 0; h < 16; ++h) {
-                if (h < G) {
-                    const uint32_t off = (uint32_t)h * 128u + ((((uint32_t)kcol >> 3) ^ ((uint32_t)h & 7u)) << 4) + ((uint32_t)kcol & 7u) * 2u;
-                    *reinterpret_cast<uint16_t*>(pb + off) = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(pk[h])));
-                }
+            for (int h = 0; h < G; ++h) {
+                const uint32_t off = (uint32_t)h * 128u + ((((uint32_t)kcol >> 3) ^ (uint32_t)(h & 7)) << 4) + ((uint32_t)kcol & 7u) * 2u;
+                *reinterpret_cast<uint16_t*>(pb + off) = __bfloat16_as_ushort(__float2bfloat16_rn(pv[h]));
             }
+            if (row == 0) TRACE(7, j);
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&sh->p_full[b]);
+            if (row == 0) TRACE(4, j);
         }
 
         // ---- epilogue: total row sums (one reduction), then O^T lanes
-        float l_tot[16];
+        float l_tot[G];
 #pragma unroll
-        for (int h = 0; h < 16; ++h) {
+        for (int h = 0; h < G; ++h) {
             float v = l_thr[h];
-            if (h < G) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            }
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == h) sh->lsum[q4][h] = v;
         }
         named_bar_sync(1, 128);
 #pragma unroll
-        for (int h = 0; h < 16; ++h) l_tot[h] = sh->lsum[0][h] + sh->lsum[1][h] + sh->lsum[2][h] + sh->lsum[3][h];
-        uint32_t orow[16];
+        for (int h = 0; h < G; ++h) l_tot[h] = sh->lsum[0][h] + sh->lsum[1][h] + sh->lsum[2][h] + sh->lsum[3][h];
+        uint32_t orow[8];
         if (n_tiles > 0) {
             mbar_wait(&sh->o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
             tc_fence_after();
-            tmem_ld16(tmem + lane_addr + 32, orow);
+            tmem_ld8(tmem + lane_addr + 32, orow);
             tmem_wait_ld();
         } else {
 #pragma unroll
-            for (int h = 0; h < 16; ++h) orow[h] = 0u;
+            for (int h = 0; h < 8; ++h) orow[h] = 0u;
         }
         const int d = row;                         // O^T lane = head-dim index
         if (d < p.D) {
 #pragma unroll
-            for (int h = 0; h < 16; ++h) {
-                if (h >= G) break;
+            for (int h = 0; h < G; ++h) {
                 const int hq = head * G + h;
                 if (p.num_splits == 1) {
                     const float inv = l_tot[h] > 0.f ? 1.0f / l_tot[h] : 0.f;
@@ -282,8 +317,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (p.num_splits > 1) {
 #pragma unroll
-            for (int h = 0; h < 16; ++h)
-                if (row == h && h < G) p.part_ml[(int64_t)split * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
+            for (int h = 0; h < G; ++h)
+                if (row == h) p.part_ml[(int64_t)split * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
         }
     }
 
@@ -291,6 +326,44 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     if (warp == 1) tmem_dealloc<64>(tmem);
 }
+
+template <int G>
+static int launch_decode(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", DEC_SMEM, cudaGetErrorString(e));
+            return SVLM_ECUDA;
+        }
+        attr_done = true;
+    }
+    attn_decode_kernel<G><<<grid, DEC_THREADS, DEC_SMEM, st>>>(tq, tk, tv, p);
+    return launch_status("attn_decode_kernel");
+}
+
+static int launch_decode_g(int G, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid,
+                           cudaStream_t st) {
+    switch (G) {
+        case 1: return launch_decode<1>(tq, tk, tv, p, grid, st);
+        case 2: return launch_decode<2>(tq, tk, tv, p, grid, st);
+        case 3: return launch_decode<3>(tq, tk, tv, p, grid, st);
+        case 4: return launch_decode<4>(tq, tk, tv, p, grid, st);
+        case 5: return launch_decode<5>(tq, tk, tv, p, grid, st);
+        case 6: return launch_decode<6>(tq, tk, tv, p, grid, st);
+        case 7: return launch_decode<7>(tq, tk, tv, p, grid, st);
+        case 8: return launch_decode<8>(tq, tk, tv, p, grid, st);
+        default: set_error("decode attention supports 1..8 query heads per kv head (got %d)", G); return SVLM_EINVAL;
+    }
+}
+
+#ifdef SVLM_TRACE
+#include <stdlib.h>
+static void* getenv_ptr(const char* name) {
+    const char* v = getenv(name);
+    return v ? (void*)strtoull(v, nullptr, 0) : nullptr;
+}
+#endif
 
 int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
                        const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st) {
@@ -320,17 +393,10 @@ int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const v
     p.part_o = (float*)workspace;
     p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + (size_t)num_splits * q_heads * D) : nullptr;
     p.scale_log2 = scale * 1.4426950408889634f;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", DEC_SMEM, cudaGetErrorString(e));
-            return SVLM_ECUDA;
-        }
-        attr_done = true;
-    }
-    attn_decode_kernel<<<dim3(num_splits, H), DEC_THREADS, DEC_SMEM, st>>>(tq, tk, tv, p);
-    if ((rc = launch_status("attn_decode_kernel"))) return rc;
+#ifdef SVLM_TRACE
+    p.trace = (unsigned long long*)getenv_ptr("SVLM_TRACE_PTR");
+#endif
+    if ((rc = launch_decode_g(G, tq, tk, tv, p, dim3(num_splits, H), st))) return rc;
     if (num_splits > 1) {
         attn_combine_kernel<<<q_heads, 128, 0, st>>>(p.part_o, p.part_ml, p.out, q_heads, D, num_splits);
         return launch_status("attn_combine_kernel");

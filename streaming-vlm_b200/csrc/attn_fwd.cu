@@ -125,28 +125,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0 && n_tiles > 0) {
-            const uint32_t q_bytes = 2u * 128u * (uint32_t)(p.G * p.tpt);
-            mbar_arrive_expect_tx(&bars->q_full, q_bytes);
-            tma_load_4d(sQ, &tmQ, &bars->q_full, 0, 0, tok0, head);
-            tma_load_4d(sQ + PANEL_BYTES, &tmQ, &bars->q_full, 64, 0, tok0, head);
+        // whole warp in uniform control flow, one elected lane issues
+        if (n_tiles > 0) {
+            if (elect_one()) {
+                const uint32_t q_bytes = 2u * 128u * (uint32_t)(p.G * p.tpt);
+                mbar_arrive_expect_tx(&bars->q_full, q_bytes);
+                tma_load_4d(sQ, &tmQ, &bars->q_full, 0, 0, tok0, head);
+                tma_load_4d(sQ + PANEL_BYTES, &tmQ, &bars->q_full, 64, 0, tok0, head);
+            }
+            __syncwarp();
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % ATT_STAGES;
                 const uint32_t ph = (j / ATT_STAGES) & 1;
                 const int row = (my_begin + j) * BN;
                 mbar_wait(&bars->k_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->k_full[s], TILE_BYTES);
-                tma_load_3d(sK + s * TILE_BYTES, &tmK, &bars->k_full[s], 0, row, kv_coord);
-                tma_load_3d(sK + s * TILE_BYTES + PANEL_BYTES, &tmK, &bars->k_full[s], 64, row, kv_coord);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->k_full[s], TILE_BYTES);
+                    tma_load_3d(sK + s * TILE_BYTES, &tmK, &bars->k_full[s], 0, row, kv_coord);
+                    tma_load_3d(sK + s * TILE_BYTES + PANEL_BYTES, &tmK, &bars->k_full[s], 64, row, kv_coord);
+                }
+                __syncwarp();
                 mbar_wait(&bars->v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->v_full[s], TILE_BYTES);
-                tma_load_3d(sV + s * TILE_BYTES, &tmV, &bars->v_full[s], 0, row, kv_coord);
-                tma_load_3d(sV + s * TILE_BYTES + PANEL_BYTES, &tmV, &bars->v_full[s], 64, row, kv_coord);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars->v_full[s], TILE_BYTES);
+                    tma_load_3d(sV + s * TILE_BYTES, &tmV, &bars->v_full[s], 0, row, kv_coord);
+                    tma_load_3d(sV + s * TILE_BYTES + PANEL_BYTES, &tmV, &bars->v_full[s], 64, row, kv_coord);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // =========================== UMMA issuer ===========================
-        if (lane == 0 && n_tiles > 0) {
+        // whole warp in uniform control flow, one elected lane issues (see attn_decode.cu for why not `if (lane == 0)`)
+        if (n_tiles > 0) {
             const uint32_t q_addr = smem_u32(sQ);
             auto issue_qk = [&](int stage, int buf) {
                 const uint32_t k_addr = smem_u32(sK + stage * TILE_BYTES);
@@ -168,25 +179,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(&bars->q_full, 0);
             mbar_wait(&bars->k_full[0], 0);
             tc_fence_after();
-            issue_qk(0, 0);
-            umma_commit(&bars->k_empty[0]);
-            umma_commit(&bars->s_full[0]);
+            if (elect_one()) {
+                issue_qk(0, 0);
+                umma_commit(&bars->k_empty[0]);
+                umma_commit(&bars->s_full[0]);
+            }
+            __syncwarp();
             for (int j = 0; j < n_tiles; ++j) {
                 if (j + 1 < n_tiles) {
                     const int s1 = (j + 1) % ATT_STAGES;
                     mbar_wait(&bars->k_full[s1], ((j + 1) / ATT_STAGES) & 1);
                     tc_fence_after();
-                    issue_qk(s1, (j + 1) & 1);
-                    umma_commit(&bars->k_empty[s1]);
-                    umma_commit(&bars->s_full[(j + 1) & 1]);
+                    if (elect_one()) {
+                        issue_qk(s1, (j + 1) & 1);
+                        umma_commit(&bars->k_empty[s1]);
+                        umma_commit(&bars->s_full[(j + 1) & 1]);
+                    }
+                    __syncwarp();
                 }
                 const int s = j % ATT_STAGES;
                 mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);
                 mbar_wait(&bars->v_full[s], (j / ATT_STAGES) & 1);
                 tc_fence_after();
-                issue_pv(s, j & 1, j > 0);
-                umma_commit(&bars->v_empty[s]);
-                umma_commit(&bars->o_done[j & 1]);
+                if (elect_one()) {
+                    issue_pv(s, j & 1, j > 0);
+                    umma_commit(&bars->v_empty[s]);
+                    umma_commit(&bars->o_done[j & 1]);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -429,7 +449,7 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
     SVLM_REQUIRE(G <= 128, "group size %d too large", G);
     const size_t need = svlm_attn_workspace_bytes(n_q_tokens, q_heads, D, num_splits);
     SVLM_REQUIRE(num_splits == 1 || (workspace != nullptr && workspace_bytes >= need), "workspace too small: need %zu bytes", need);
-    if (n_q_tokens == 1 && G <= 16)   // decode: swap-AB kernel (attn_decode.cu)
+    if (n_q_tokens == 1 && G <= 8)    // decode: swap-AB kernel (attn_decode.cu)
         return attn_decode_launch(arena, buffer, layer, q, out, q_heads, kv_len, kv_len_dev, num_splits, workspace, scale, (cudaStream_t)stream);
 
     ArenaDims ad{arena->layers, H, D, arena->capacity};

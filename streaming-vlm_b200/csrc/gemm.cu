@@ -62,30 +62,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                mbar_wait(&empty[s], ((kb / Cfg::STAGES) & 1) ^ 1);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+            const int s = kb % Cfg::STAGES;
+            mbar_wait(&empty[s], ((kb / Cfg::STAGES) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::W_BYTES);
                 tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, &full[s], kb * GEMM_BK, m0);
                 tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, &full[s], kb * GEMM_BK, n0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                mbar_wait(&full[s], (kb / Cfg::STAGES) & 1);
-                tc_fence_after();
+        // whole warp in uniform control flow, one elected lane issues (descriptors stay in uniform registers)
+        constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+            const int s = kb % Cfg::STAGES;
+            mbar_wait(&full[s], (kb / Cfg::STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t a = smem_u32(sA + s * Cfg::A_BYTES), w = smem_u32(sW + s * Cfg::W_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < GEMM_BK / 16; ++kk)
                     umma_ss(tmem, umma_desc_sw128(a + kk * 32, 16, 1024), umma_desc_sw128(w + kk * 32, 16, 1024), IDESC,
                             (kb > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(&empty[s]);
+                if (kb == k_blocks - 1) umma_commit(acc_done);
             }
-            umma_commit(acc_done);
+            __syncwarp();
         }
     } else {
         const int q4 = warp & 3;
