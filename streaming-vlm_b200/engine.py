@@ -120,8 +120,11 @@ class StreamingEngine:
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
         self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._pf_ids = torch.zeros(1024, dtype=torch.int64, device=dev)
         self.suppress_u8 = None if self.suppress is None else self.suppress.to(torch.uint8).contiguous()
         self._vit_plans = {}
+        self._vit_graphs = {}
+        self._pf_graphs = {}
         # session state (reference: inference.py:297-303)
         self.prev_ids = None
         self.history, self.clips, self.pixels, self.grids = [], [], [], []
@@ -167,6 +170,14 @@ class StreamingEngine:
         self.lm_head = mv(w.pop("lm_head.weight"))
 
     # ------------------------------------------------------------------ small helpers
+    def _mark(self, name):
+        """Optional phase timeline (CUDA events on the current stream), enabled by `self.phase_marks = []`."""
+        marks = getattr(self, "phase_marks", None)
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e, time.perf_counter()))
+
     def _rmsnorm(self, x, w, eps=1e-6):
         out = torch.empty_like(x)
         _abi.rmsnorm(x, w, out, eps)
@@ -175,11 +186,40 @@ class StreamingEngine:
 
     # ------------------------------------------------------------------ ViT (vision_forward.py:57-101)
     def vision_forward(self, pixels: torch.Tensor, grid, taps=None):
+        """ViT on one chunk.  With `use_graph` the whole tower (~420 launches, static shapes per grid) is one CUDA-graph
+        replay: the eager tower is host-launch-bound (4.6 ms of Python for 2 ms of GPU work at the 7B geometry)."""
         g = self.geo
         grid = tuple(int(x) for x in grid)
         plan = self._vit_plans.get(grid)
         if plan is None:
             plan = self._vit_plans[grid] = _VitPlan(grid, g, self.device)
+        if not self.use_graph or taps is not None:
+            return self._vision_body(pixels, plan, taps)
+        key = (grid, pixels.dtype)
+        entry = self._vit_graphs.get(key)
+        if entry is None:
+            px_in = torch.zeros_like(pixels)
+            px_in.copy_(pixels)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._vision_body(px_in, plan, None)            # warm-up outside capture
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            before = self.launches
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                out = self._vision_body(px_in, plan, None)
+            entry = self._vit_graphs[key] = (gr, px_in, out, self.launches - before)
+            self.launches = before
+        gr, px_in, out, n_launch = entry
+        px_in.copy_(pixels, non_blocking=True)
+        gr.replay()
+        self.launches += n_launch
+        return out
+
+    def _vision_body(self, pixels, plan, taps=None):
+        g = self.geo
         n, unit = plan.n, g.spatial_merge_size ** 2
         heads, hd = g.vit_heads, g.vit_hidden // g.vit_heads
         x = F.linear(pixels.to(torch.bfloat16), self.w_patch)
@@ -207,7 +247,7 @@ class StreamingEngine:
         return out
 
     # ------------------------------------------------------------------ LLM layers (language_forward.py:143-305)
-    def _layer(self, x, li, t, start, kv_len, splits, decode, taps=None):
+    def _layer(self, x, li, t, start, kv_len, splits, decode, taps=None, dev_start=False):
         g, c, L = self.geo, self.cache, self.layers[li]
         hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
         h = self._rmsnorm(x, L["ln1"], g.rms_eps)
@@ -217,11 +257,14 @@ class StreamingEngine:
         if decode:
             _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, 0, None, c.cos_table, c.sin_table, c.section,
                                  start_dev=self.kv_len_dev, text_pos_dev=c.next_pos)
+        elif dev_start:      # graph-captured prefill: arena row and kv length come from device memory
+            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, 0, c.pos, c.cos_table, c.sin_table, c.section,
+                                 start_dev=self.kv_len_dev)
         else:
             _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, start, c.pos, c.cos_table, c.sin_table, c.section)
         o = torch.empty(t, hq, d, dtype=torch.bfloat16, device=self.device)
         _abi.attn_causal(c.view, c.cur, li, q_rot, o, t, hq, kv_len, self.scale, splits, self.ws if splits > 1 else None,
-                         kv_len_dev=self.kv_after_dev if decode else None)
+                         kv_len_dev=self.kv_after_dev if (decode or dev_start) else None)
         self.launches += 2 + (1 if splits > 1 else 0)
         if taps is not None:
             taps.setdefault("attn_out", []).append(o.view(t, -1))
@@ -239,31 +282,62 @@ class StreamingEngine:
         return logits
 
     def prefill(self, new_ids, video_embeds, taps=None):
-        """Forward over the uncached ids (already uploaded as the tail of `cache.ids_dev`, positions in `cache.pos`)."""
+        """Forward over the uncached ids (already uploaded as the tail of `cache.ids_dev`, positions in `cache.pos`).
+        With `use_graph`, one CUDA graph per (T, video-token layout, live buffer): the arena row and the kv length are
+        read from device memory, so the same graph serves every steady-state chunk."""
         c, g = self.cache, self.geo
         t, start = len(new_ids), c.seq_len
         if start + t > c.capacity:
             raise RuntimeError(f"sequence of {start + t} tokens exceeds the arena capacity {c.capacity}")
-        x = F.embedding(c.ids_dev[start:start + t], self.embed)
+        runs = ()
         if video_embeds is not None:
             ids_np = np.asarray(new_ids)
             where = np.flatnonzero(ids_np == VIDEO_PAD)
             if where.size != video_embeds.shape[0]:
                 raise ValueError(f"Video features and video tokens do not match: tokens: {where.size}, features {video_embeds.shape[0]}")
             brk = np.flatnonzero(np.diff(where) != 1) + 1
-            o = 0
-            for a, b in zip(np.concatenate([[0], brk]), np.concatenate([brk, [where.size]])):
-                x[where[a]:where[a] + (b - a)] = video_embeds[o:o + (b - a)]
-                o += b - a
-        splits = self.prefill_splits or (1 if (-(-t // (128 // g.group))) * g.num_kv_heads >= 74 or start + t < 2048 else 2)
-        for li in range(g.num_layers):
-            x = self._layer(x, li, t, start, start + t, splits, False, taps)
+            runs = tuple((int(where[a]), int(b - a)) for a, b in zip(np.concatenate([[0], brk]), np.concatenate([brk, [where.size]])))
+        splits = self.prefill_splits or (1 if (-(-t // (128 // g.group))) * g.num_kv_heads >= 74 or start + t < 2048 or t > 512 else 2)
+        if not self.use_graph or taps is not None or t < 2 or t > self._pf_ids.numel():
+            logits = self._prefill_body(c.ids_dev[start:start + t], t, start, video_embeds, runs, splits, False, taps)
+        else:
+            self._pf_ids[:t].copy_(c.ids_dev[start:start + t])
+            self.kv_len_dev.fill_(start)
+            self.kv_after_dev.fill_(start + t)
+            key = (t, runs, splits, c.cur, None if video_embeds is None else video_embeds.data_ptr())
+            entry = self._pf_graphs.get(key)
+            if entry is None:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._prefill_body(self._pf_ids[:t], t, start, video_embeds, runs, splits, True, None)   # warm-up
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                before = self.launches
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    out = self._prefill_body(self._pf_ids[:t], t, start, video_embeds, runs, splits, True, None)
+                entry = self._pf_graphs[key] = (gr, out, self.launches - before)
+                self.launches = before
+            gr, logits, n_launch = entry
+            gr.replay()
+            self.launches += n_launch
         c.seq_len = start + t
         c._seen_tokens += t
-        logits = self._logits(x[-1:])
         if taps is not None:
             taps["logits"] = logits[0]
         return logits
+
+    def _prefill_body(self, ids, t, start, video_embeds, runs, splits, dev_start, taps):
+        g = self.geo
+        x = F.embedding(ids, self.embed)
+        o = 0
+        for a, n in runs:
+            x[a:a + n] = video_embeds[o:o + n]
+            o += n
+        for li in range(g.num_layers):
+            x = self._layer(x, li, t, start, self.cache.capacity if dev_start else start + t, splits, False, taps, dev_start)
+        return self._logits(x[-1:])
 
     # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
     def _decode_body(self):
@@ -328,11 +402,14 @@ class StreamingEngine:
         c = self.cache
         input_len = len(ids_full)
         new_ids = ids_full[c.seq_len:]
+        self._mark("vit_start")
         video = self.vision_forward(pixels, grid, taps) if pixels is not None else None
         if taps is not None and video is not None:
             taps["video_embeds"] = video
+        self._mark("prefill_start")
         logits = self.prefill(new_ids, video, taps)
         self.tok_dev.copy_(torch.argmax(logits, dim=-1))
+        self._mark("decode_start")
         self.kv_len_dev.fill_(c.seq_len)
         self.kv_after_dev.fill_(c.seq_len + 1)
         seq = list(ids_full)
@@ -351,6 +428,7 @@ class StreamingEngine:
                 break
             self.decode_step()
             n_fwd += 1
+        self._mark("decode_end")
         return seq, n_fwd
 
     def load_state(self, state, seed=0):
@@ -377,6 +455,7 @@ class StreamingEngine:
         i, c = self.i, self.cache
         if sync_timing:
             torch.cuda.synchronize()
+        self._mark("step_start")
         t0 = time.perf_counter()
         runs, plan = None, None
         if self.prev_ids is not None:
