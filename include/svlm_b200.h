@@ -158,6 +158,18 @@ int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int 
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (6b) Elementwise glue of the prefill / ViT blocks, fused (bf16 in / out, fp32 arithmetic).
+ * svlm_add_rmsnorm replaces `hidden = residual + x` followed by the next RMSNorm
+ *   (qwen2_5/language_forward.py:290-295, qwen2_5/vision_forward.py:46-52): out_sum = bf16(a + b) (b and out_sum may
+ *   be NULL = plain RMSNorm), out_norm = RMSNorm(out_sum) * weight.
+ * svlm_swiglu replaces `act_fn(gate_proj(x)) * up_proj(x)` of Qwen2MLP / Qwen2_5_VLMLP on the fused [gate | up]
+ *   GEMM output: gate_up [rows][2M] -> out [rows][M].
+ * ------------------------------------------------------------------------------------- */
+int svlm_add_rmsnorm(const void* a, const void* b, const void* weight, void* out_sum, void* out_norm, int rows, int cols,
+                     float eps, void* stream);
+int svlm_swiglu(const void* gate_up, void* out, int rows, int M, int64_t gate_up_row_stride, int64_t out_row_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (7) Decode-step (one token) weight-streaming GEMV with fused RMSNorm prologue and epilogue; HBM-bound.
  * Replaces, for q_len == 1: the nn.Linear / RMSNorm / SiLU / residual-add calls of
  *           qwen2_5/language_forward.py:175-177 (q/k/v_proj after input_layernorm, :277), :255 (o_proj) + :290

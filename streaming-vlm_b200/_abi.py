@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_gemv_bf16", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
 
@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
     L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
     L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
     L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
+    L.svlm_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_float, vp]
+    L.svlm_swiglu.argtypes = [vp, vp, c_int, c_int, c_int64, c_int64, vp]
     L.svlm_gemv_bf16.argtypes = [vp, vp, vp, c_float, vp, vp, vp, c_int, c_int, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
@@ -208,6 +210,21 @@ def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, 
     check(lib().svlm_lm_head_argmax(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
                                     key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
                                     next_pos.data_ptr(), _stream()), "svlm_lm_head_argmax")
+
+
+def add_rmsnorm(a, b, weight, out_sum, out_norm, eps: float):
+    """out_sum = a + b (both optional), out_norm = RMSNorm(out_sum) * weight."""
+    _req_cuda(a, weight, out_norm)
+    rows, cols = a.shape
+    check(lib().svlm_add_rmsnorm(a.data_ptr(), _ptr(b), weight.data_ptr(), _ptr(out_sum), out_norm.data_ptr(), rows, cols, eps,
+                                 _stream()), "svlm_add_rmsnorm")
+
+
+def swiglu(gate_up, out):
+    _req_cuda(gate_up, out)
+    rows, m = out.shape
+    assert gate_up.shape[1] == 2 * m and gate_up.stride(1) == 1 and out.stride(1) == 1
+    check(lib().svlm_swiglu(gate_up.data_ptr(), out.data_ptr(), rows, m, gate_up.stride(0), out.stride(0), _stream()), "svlm_swiglu")
 
 
 def rmsnorm(x, weight, out, eps: float):

@@ -315,42 +315,82 @@ __global__ void __launch_bounds__(256) vit_rope_kernel(uint16_t* __restrict__ qk
 }
 
 // ---------------------------------------------------------------------------------------------------
-// rmsnorm: one warp per row.  out = bf16( w * bf16( x * rsqrt(mean(x^2) + eps) ) )   (HF Qwen2_5_VLRMSNorm)
+// add_rmsnorm: one CTA (128 threads) per row, the row stays in registers (single pass over global memory).
+//   s = a (+ b)                          optional residual add, rounded to bf16 (the reference's `residual + x`)
+//   out_norm = bf16( w * bf16( s * rsqrt(mean(s^2) + eps) ) )          (HF Qwen2_5_VLRMSNorm)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
-                                                       uint16_t* __restrict__ out, int rows, int cols, float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const uint16_t* xr = x + (int64_t)row * cols;
+constexpr int RN_MAX_VEC = 8;     // cols <= 128 threads * 8 vectors * 8 elements = 8192
+__global__ void __launch_bounds__(128) add_rmsnorm_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b,
+                                                           const uint16_t* __restrict__ w, uint16_t* __restrict__ out_sum,
+                                                           uint16_t* __restrict__ out_norm, int cols, float eps) {
+    __shared__ float red[4];
+    const int64_t base = (int64_t)blockIdx.x * cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 v[RN_MAX_VEC];
     float ss = 0.f;
-    for (int c = lane * 8; c < cols; c += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
-        const uint32_t* p = &v.x;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float a = bf16_lo(p[i]), b = bf16_hi(p[i]);
-            ss += a * a + b * b;
+    for (int i = 0; i < RN_MAX_VEC; ++i) {
+        const int c = (i * 128 + threadIdx.x) * 8;
+        if (c < cols) {
+            v[i] = *reinterpret_cast<const uint4*>(a + base + c);
+            if (b) {
+                const uint4 y = *reinterpret_cast<const uint4*>(b + base + c);
+                uint32_t* p = &v[i].x;
+                const uint32_t* q = &y.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] = pack_bf16(bf16_lo(p[k]) + bf16_lo(q[k]), bf16_hi(p[k]) + bf16_hi(q[k]));
+                if (out_sum) *reinterpret_cast<uint4*>(out_sum + base + c) = v[i];
+            }
+            const uint32_t* p = &v[i].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float x0 = bf16_lo(p[k]), x1 = bf16_hi(p[k]); ss += x0 * x0 + x1 * x1; }
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-    const float r = rsqrtf(ss / (float)cols + eps);
-    uint16_t* orow = out + (int64_t)row * cols;
-    for (int c = lane * 8; c < cols; c += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
-        const uint4 wv = *reinterpret_cast<const uint4*>(w + c);
-        const uint32_t* p = &v.x;
-        const uint32_t* q = &wv.x;
-        uint4 o;
-        uint32_t* po = &o.x;
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    const float r = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)cols + eps);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float a = round_bf16(bf16_lo(p[i]) * r), b = round_bf16(bf16_hi(p[i]) * r);
-            po[i] = pack_bf16(bf16_lo(q[i]) * a, bf16_hi(q[i]) * b);
+    for (int i = 0; i < RN_MAX_VEC; ++i) {
+        const int c = (i * 128 + threadIdx.x) * 8;
+        if (c < cols) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(w + c);
+            const uint32_t* p = &v[i].x;
+            const uint32_t* q = &wv.x;
+            uint4 o;
+            uint32_t* po = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                po[k] = pack_bf16(bf16_lo(q[k]) * round_bf16(bf16_lo(p[k]) * r), bf16_hi(q[k]) * round_bf16(bf16_hi(p[k]) * r));
+            *reinterpret_cast<uint4*>(out_norm + base + c) = o;
         }
-        *reinterpret_cast<uint4*>(orow + c) = o;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// swiglu: gu [rows][2*M] (gate columns then up columns, the fused gate/up GEMM output) -> out [rows][M],
+//   out = bf16( bf16(silu(gate)) * up )      (Qwen2MLP / Qwen2_5_VLMLP act_fn(gate_proj(x)) * up_proj(x))
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swiglu_kernel(const uint16_t* __restrict__ gu, uint16_t* __restrict__ out, int rows, int M,
+                                                      int64_t gu_stride, int64_t out_stride) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vec_per_row = M / 8;
+    if (idx >= (int64_t)rows * vec_per_row) return;
+    const int r = (int)(idx / vec_per_row), c = (int)(idx % vec_per_row) * 8;
+    const uint4 gv = *reinterpret_cast<const uint4*>(gu + r * gu_stride + c);
+    const uint4 uv = *reinterpret_cast<const uint4*>(gu + r * gu_stride + M + c);
+    const uint32_t* g = &gv.x;
+    const uint32_t* u = &uv.x;
+    uint4 o;
+    uint32_t* po = &o.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float g0 = bf16_lo(g[k]), g1 = bf16_hi(g[k]);
+        const float s0 = round_bf16(g0 / (1.0f + __expf(-g0))), s1 = round_bf16(g1 / (1.0f + __expf(-g1)));
+        po[k] = pack_bf16(s0 * bf16_lo(u[k]), s1 * bf16_hi(u[k]));
+    }
+    *reinterpret_cast<uint4*>(out + r * out_stride + c) = o;
 }
 
 static int make_tables(RopeTables* t, const void* cos_table, const void* sin_table, int rows, const int32_t* sec, int D) {
@@ -455,12 +495,33 @@ extern "C" int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int 
     return launch_status("vit_rope_kernel");
 }
 
-extern "C" int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream) {
+extern "C" int svlm_add_rmsnorm(const void* a, const void* b, const void* weight, void* out_sum, void* out_norm, int rows, int cols,
+                                float eps, void* stream) {
     int rc = check_device();
     if (rc) return rc;
-    SVLM_REQUIRE(x && weight && out, "NULL tensor argument");
-    SVLM_REQUIRE(cols % 8 == 0, "cols %d must be a multiple of 8", cols);
+    SVLM_REQUIRE(a && weight && out_norm, "NULL tensor argument");
+    SVLM_REQUIRE(cols % 8 == 0 && cols <= 128 * RN_MAX_VEC * 8, "cols %d must be a multiple of 8 and <= %d", cols, 128 * RN_MAX_VEC * 8);
+    SVLM_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)weight | (uintptr_t)out_sum | (uintptr_t)out_norm) & 15) == 0,
+                 "tensors must be 16-byte aligned");
     if (rows == 0) return SVLM_OK;
-    rmsnorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, (const uint16_t*)weight, (uint16_t*)out, rows, cols, eps);
-    return launch_status("rmsnorm_kernel");
+    add_rmsnorm_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)a, (const uint16_t*)b, (const uint16_t*)weight,
+                                                               (uint16_t*)out_sum, (uint16_t*)out_norm, cols, eps);
+    return launch_status("add_rmsnorm_kernel");
+}
+
+extern "C" int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream) {
+    return svlm_add_rmsnorm(x, nullptr, weight, nullptr, out, rows, cols, eps, stream);
+}
+
+extern "C" int svlm_swiglu(const void* gate_up, void* out, int rows, int M, int64_t gate_up_row_stride, int64_t out_row_stride, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(gate_up && out, "NULL tensor argument");
+    SVLM_REQUIRE(M % 8 == 0 && gate_up_row_stride % 8 == 0 && out_row_stride % 8 == 0, "M and row strides must be multiples of 8");
+    SVLM_REQUIRE((((uintptr_t)gate_up | (uintptr_t)out) & 15) == 0, "tensors must be 16-byte aligned");
+    const int64_t total = (int64_t)rows * (M / 8);
+    if (total == 0) return SVLM_OK;
+    swiglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)gate_up, (uint16_t*)out, rows, M,
+                                                                                     gate_up_row_stride, out_row_stride);
+    return launch_status("swiglu_kernel");
 }

@@ -141,15 +141,21 @@ class StreamingEngine:
         pe = w.pop(v + "patch_embed.proj.weight")
         self.w_patch = mv(pe.reshape(pe.shape[0], -1))
         self.vit = []
+        # The ViT MLP width (3420) makes the down projection's rows 6840 B -- not 16-byte aligned, which pushes cuBLAS onto a
+        # legacy mma.sync kernel (58 us vs ~12 us).  Zero-padding the width to a multiple of 64 changes no result:
+        # silu(0) * 0 = 0 feeds zero columns of the down projection.
+        mp = -(-g.vit_mlp // 64) * 64
+        self.vit_mlp_padded = mp
+        padr = lambda t: F.pad(t, (0, 0, 0, mp - g.vit_mlp)) if t.dim() == 2 else F.pad(t, (0, mp - g.vit_mlp))
         for li in range(g.vit_depth):
             b = f"{v}blocks.{li}."
             self.vit.append(dict(
                 n1=mv(w.pop(b + "norm1.weight")), n2=mv(w.pop(b + "norm2.weight")),
                 wqkv=mv(w.pop(b + "attn.qkv.weight")), bqkv=mv(w.pop(b + "attn.qkv.bias")),
                 wproj=mv(w.pop(b + "attn.proj.weight")), bproj=mv(w.pop(b + "attn.proj.bias")),
-                wgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.weight"), w.pop(b + "mlp.up_proj.weight")], 0)),
-                bgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.bias"), w.pop(b + "mlp.up_proj.bias")], 0)),
-                wd=mv(w.pop(b + "mlp.down_proj.weight")), bd=mv(w.pop(b + "mlp.down_proj.bias"))))
+                wgu=mv(torch.cat([padr(w.pop(b + "mlp.gate_proj.weight")), padr(w.pop(b + "mlp.up_proj.weight"))], 0)),
+                bgu=mv(torch.cat([padr(w.pop(b + "mlp.gate_proj.bias")), padr(w.pop(b + "mlp.up_proj.bias"))], 0)),
+                wd=mv(F.pad(w.pop(b + "mlp.down_proj.weight"), (0, mp - g.vit_mlp))), bd=mv(w.pop(b + "mlp.down_proj.bias"))))
         self.merger = dict(ln=mv(w.pop(v + "merger.ln_q.weight")), w0=mv(w.pop(v + "merger.mlp.0.weight")),
                            b0=mv(w.pop(v + "merger.mlp.0.bias")), w2=mv(w.pop(v + "merger.mlp.2.weight")),
                            b2=mv(w.pop(v + "merger.mlp.2.bias")))
@@ -181,6 +187,24 @@ class StreamingEngine:
     def _rmsnorm(self, x, w, eps=1e-6):
         out = torch.empty_like(x)
         _abi.rmsnorm(x, w, out, eps)
+        self.launches += 1
+        return out
+
+    def _add_norm(self, x, pending, w, eps=1e-6):
+        """(x + pending, RMSNorm(x + pending) * w) in one kernel; pending=None -> (x, RMSNorm(x) * w)."""
+        h = torch.empty_like(x)
+        if pending is None:
+            _abi.add_rmsnorm(x, None, w, None, h, eps)
+            self.launches += 1
+            return x, h
+        xs = torch.empty_like(x)
+        _abi.add_rmsnorm(x, pending, w, xs, h, eps)
+        self.launches += 1
+        return xs, h
+
+    def _swiglu(self, gu, m):
+        out = torch.empty(gu.shape[0], m, dtype=gu.dtype, device=gu.device)
+        _abi.swiglu(gu, out)
         self.launches += 1
         return out
 
@@ -224,21 +248,20 @@ class StreamingEngine:
         heads, hd = g.vit_heads, g.vit_hidden // g.vit_heads
         x = F.linear(pixels.to(torch.bfloat16), self.w_patch)
         x = x.reshape(n // unit, unit, -1)[plan.order].reshape(n, -1)
+        pending = None                                      # sub-layer output not yet added to the residual stream
         for li, b in enumerate(self.vit):
             cu = plan.cu_full if li in g.fullatt_block_indexes else plan.cu_window
-            h = self._rmsnorm(x, b["n1"])
+            x, h = self._add_norm(x, pending, b["n1"])
             qkv = F.linear(h, b["wqkv"], b["bqkv"])
             _abi.vit_rope(qkv, plan.cos, plan.sin, n, heads, hd)
             o = torch.empty(n, heads, hd, dtype=torch.bfloat16, device=self.device)
             _abi.vit_attn(qkv, cu, o, n, heads, hd, hd ** -0.5)
             self.launches += 2
-            x = x + F.linear(o.view(n, -1), b["wproj"], b["bproj"])
-            h = self._rmsnorm(x, b["n2"])
+            x, h = self._add_norm(x, F.linear(o.view(n, -1), b["wproj"], b["bproj"]), b["n2"])
             gu = F.linear(h, b["wgu"], b["bgu"])
-            x = x + F.linear(F.silu(gu[:, :g.vit_mlp]) * gu[:, g.vit_mlp:], b["wd"], b["bd"])
-            if taps is not None:
-                taps.setdefault("vit_hidden", []).append(x)
-        h = self._rmsnorm(x, self.merger["ln"]).view(n // unit, -1)
+            pending = F.linear(self._swiglu(gu, self.vit_mlp_padded), b["wd"], b["bd"])
+        _, h = self._add_norm(x, pending, self.merger["ln"])
+        h = h.view(n // unit, -1)
         y = torch.empty(n // unit, self.merger["w0"].shape[0], dtype=torch.bfloat16, device=self.device)
         _abi.gemm_bf16(h, self.merger["w0"], self.merger["b0"], y, act=1)
         out = torch.empty(n // unit, g.hidden, dtype=torch.bfloat16, device=self.device)
@@ -247,35 +270,33 @@ class StreamingEngine:
         return out
 
     # ------------------------------------------------------------------ LLM layers (language_forward.py:143-305)
-    def _layer(self, x, li, t, start, kv_len, splits, decode, taps=None, dev_start=False):
+    def _layer(self, x, pending, li, t, start, kv_len, splits, taps=None, dev_start=False):
+        """One decoder layer of the chunk prefill.  `pending` is the previous layer's MLP output, added to the residual
+        stream inside the fused add+RMSNorm kernel; returns (x, pending) in the same convention."""
         g, c, L = self.geo, self.cache, self.layers[li]
         hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
-        h = self._rmsnorm(x, L["ln1"], g.rms_eps)
+        x, h = self._add_norm(x, pending, L["ln1"], g.rms_eps)
         qkv = F.linear(h, L["wqkv"], L["bqkv"])
         q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
         q_rot = torch.empty(t, hq, d, dtype=torch.bfloat16, device=self.device)
-        if decode:
-            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, 0, None, c.cos_table, c.sin_table, c.section,
-                                 start_dev=self.kv_len_dev, text_pos_dev=c.next_pos)
-        elif dev_start:      # graph-captured prefill: arena row and kv length come from device memory
+        if dev_start:        # graph-captured prefill: arena row and kv length come from device memory
             _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, 0, c.pos, c.cos_table, c.sin_table, c.section,
                                  start_dev=self.kv_len_dev)
         else:
             _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, t, hq, q_rot, start, c.pos, c.cos_table, c.sin_table, c.section)
         o = torch.empty(t, hq, d, dtype=torch.bfloat16, device=self.device)
         _abi.attn_causal(c.view, c.cur, li, q_rot, o, t, hq, kv_len, self.scale, splits, self.ws if splits > 1 else None,
-                         kv_len_dev=self.kv_after_dev if (decode or dev_start) else None)
+                         kv_len_dev=self.kv_after_dev if dev_start else None)
         self.launches += 2 + (1 if splits > 1 else 0)
         if taps is not None:
             taps.setdefault("attn_out", []).append(o.view(t, -1))
             taps.setdefault("q_rot", []).append(q_rot)
-        x = x + F.linear(o.view(t, -1), L["wo"])
-        h = self._rmsnorm(x, L["ln2"], g.rms_eps)
+        x, h = self._add_norm(x, F.linear(o.view(t, -1), L["wo"]), L["ln2"], g.rms_eps)
         gu = F.linear(h, L["wgu"])
-        return x + F.linear(F.silu(gu[:, :g.mlp]) * gu[:, g.mlp:], L["wd"])
+        return x, F.linear(self._swiglu(gu, g.mlp), L["wd"])
 
-    def _logits(self, x_last):
-        h = self._rmsnorm(x_last, self.norm, self.geo.rms_eps)
+    def _logits(self, x_last, pending_last=None):
+        _, h = self._add_norm(x_last, pending_last, self.norm, self.geo.rms_eps)
         logits = F.linear(h, self.lm_head).float()
         if self.suppress is not None:
             logits = logits.masked_fill(self.suppress, float("-inf"))
@@ -335,9 +356,10 @@ class StreamingEngine:
         for a, n in runs:
             x[a:a + n] = video_embeds[o:o + n]
             o += n
+        pending = None
         for li in range(g.num_layers):
-            x = self._layer(x, li, t, start, self.cache.capacity if dev_start else start + t, splits, False, taps, dev_start)
-        return self._logits(x[-1:])
+            x, pending = self._layer(x, pending, li, t, start, self.cache.capacity if dev_start else start + t, splits, taps, dev_start)
+        return self._logits(x[-1:].contiguous(), pending[-1:].contiguous())
 
     # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
     def _decode_body(self):

@@ -352,3 +352,23 @@ def test_lm_head_argmax(abi):
         assert logits[t] >= logits.max() - 0.016 * abs(float(logits.max())), (t, int(logits.argmax()))
         assert t < 151643
     assert cnt.tolist() == [104, 105, 11] and key.item() == 0
+
+
+def test_add_rmsnorm_and_swiglu(abi):
+    g = torch.Generator().manual_seed(8)
+    for rows, cols in [(278, 3584), (1024, 1280), (3, 512), (5, 8192)]:
+        a = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
+        b = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
+        w = (1 + 0.1 * torch.randn(cols, generator=g)).to(torch.bfloat16)
+        s_out = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+        n_out = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+        abi.add_rmsnorm(a.to(DEV), b.to(DEV), w.to(DEV), s_out, n_out, 1e-6)
+        ref_s = a + b
+        assert torch.equal(bits(s_out.cpu()), bits(ref_s))
+        torch.testing.assert_close(n_out.cpu().float(), o_vit.rmsnorm(ref_s, w, 1e-6).float(), rtol=1.6e-2, atol=1e-3)
+    for rows, m in [(278, 18944), (1024, 3456), (2, 64)]:
+        gu = torch.randn(rows, 2 * m, generator=g).to(torch.bfloat16)
+        out = torch.empty(rows, m, dtype=torch.bfloat16, device=DEV)
+        abi.swiglu(gu.to(DEV), out)
+        ref = torch.nn.functional.silu(gu[:, :m]) * gu[:, m:]
+        torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=1.6e-2, atol=1e-3)
