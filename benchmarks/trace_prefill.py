@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Developer tool: per-tile clock64 timeline of the prefill attention kernel (-DSVLM_TRACE build)."""
+import math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from streaming_vlm_b200 import _abi
+_abi.LIB_PATH = os.path.join(ROOT, "benchmarks", "_trace", "libsvlm_trace.so")
+from streaming_vlm_b200.config import QWEN25VL_7B as G
+from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+tq, splits = 276, 2
+dev = torch.device("cuda")
+c = StreamingCache(G, n + 512, dev)
+c.arena[0].normal_(0, 0.5)
+HQ, D = G.num_heads, G.head_dim
+mt = -(-tq // 18)
+trace = torch.zeros(splits * 4 * mt * 32 * 16, dtype=torch.int64, device=dev)
+os.environ["SVLM_TRACE_PTR"] = str(trace.data_ptr())
+q = torch.randn(tq, HQ, D, device=dev).to(torch.bfloat16); o = torch.empty_like(q)
+ws = torch.zeros(_abi.attn_workspace_bytes(tq, HQ, D, splits) // 4 + 16, dtype=torch.float32, device=dev)
+for it in range(3):
+    _abi.attn_causal(c.view, 0, it, q, o, tq, HQ, n, 1 / math.sqrt(D), splits, ws)
+torch.cuda.synchronize()
+t = trace.view(splits, 4, mt, 32, 16).cpu()
+tt = t[0, 1, 3]
+nt = int((tt[:, 1] > 0).sum())
+base = int(tt[0, 0])
+ev = ["top", "s_seen", "ld", "bar_issue", "arrived"]
+for j in range(4, min(nt, 9)):
+    for name, o in (("w2 smsp2 half0", 0), ("w6 smsp2 half1", 5), ("w4 smsp0 half0", 10)):
+        print(j, name, " ".join(f"{ev[e]}={int(tt[j, o + e]) - base:6d}" for e in range(5)))

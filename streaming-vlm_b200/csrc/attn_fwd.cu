@@ -17,6 +17,7 @@
 //              the PV UMMA), rescale O in TMEM only when the max moved by more than 2^8; epilogue O / l.
 // TMEM: S0 [0,128) | S1 [128,256) | O [256,384) columns, fp32, 128 lanes.
 #include <math.h>
+#include <stdlib.h>
 
 #include "attn_common.cuh"
 
@@ -27,8 +28,8 @@ constexpr int BN = 128;
 constexpr int ATT_STAGES = 3;
 constexpr int PANEL_BYTES = 128 * 128;          // 128 rows x 64 bf16
 constexpr int TILE_BYTES = 2 * PANEL_BYTES;     // 128 rows x 128 bf16
-constexpr int ATT_THREADS = 192;
-constexpr int ATT_SMEM = 1024 + TILE_BYTES * (1 + 2 * ATT_STAGES) + 512;
+constexpr int ATT_THREADS = 320;          // warp 0 TMA, warp 1 UMMA, warps 2-5 / 6-9 softmax column halves
+constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 * ATT_STAGES) + 3072;   // = 232448 B, the sm_100 per-CTA maximum
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
 
 constexpr int MODE_CAUSAL = 0;
@@ -47,7 +48,14 @@ struct AttnParams {
     float* part_o;             // fp32 [splits][Tq][Hq][D]   (num_splits > 1)
     float2* part_ml;           // (m, l) [splits][Tq][Hq]
     float scale_log2;          // softmax scale * log2(e)
+    unsigned long long* trace; // SVLM_TRACE builds only
 };
+
+#ifdef SVLM_TRACE
+#define ATRACE(ev, tile) do { if (p.trace && (tile) < 32) p.trace[((((blockIdx.z * gridDim.y) + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (tile)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define ATRACE(ev, tile) do { } while (0)
+#endif
 
 struct AttnBars {
     uint64_t q_full;
@@ -56,7 +64,10 @@ struct AttnBars {
     uint64_t s_full[2], p_full[2];
     uint64_t o_done[2];   // PV(j) completion alternates between the two (see the wait in the softmax warps)
     uint32_t tmem_base;
+    float xmax[2][2][128];   // [tile parity][column half][row]: half-row maxima exchanged between the two softmax groups
+                             // (xmax[0] doubles as the row-sum exchange buffer in the epilogue)
 };
+static_assert(sizeof(AttnBars) <= 3072, "AttnBars must fit behind the tiles");
 
 __device__ __forceinline__ int find_seq(const int32_t* cu, int n_seqs, int tok) {
     int lo = 0, hi = n_seqs - 1;           // largest s with cu[s] <= tok
@@ -71,8 +82,8 @@ template <int MODE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];   // the kernel has no static shared memory, so the window starts 1024-aligned
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();       // (128B-swizzle atoms need it; checked rather than assumed)
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TILE_BYTES;
     uint8_t* sV = sK + ATT_STAGES * TILE_BYTES;
@@ -88,7 +99,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
             mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->p_full[b], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->p_full[b], 256); }
         mbar_init(&bars->o_done[0], 1); mbar_init(&bars->o_done[1], 1);
         fence_barrier_init();
     }
@@ -139,6 +150,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint32_t ph = (j / ATT_STAGES) & 1;
                 const int row = (my_begin + j) * BN;
                 mbar_wait(&bars->k_empty[s], ph ^ 1);
+                if (lane == 0) ATRACE(7, j);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars->k_full[s], TILE_BYTES);
                     tma_load_3d(sK + s * TILE_BYTES, &tmK, &bars->k_full[s], 0, row, kv_coord);
@@ -198,7 +210,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     __syncwarp();
                 }
                 const int s = j % ATT_STAGES;
+                if (lane == 0) ATRACE(5, j);
                 mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);
+                if (lane == 0) ATRACE(6, j);
                 mbar_wait(&bars->v_full[s], (j / ATT_STAGES) & 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -211,7 +225,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else {
         // =========================== softmax + epilogue ===========================
+        // Two groups of four warps split the 128 score columns of every row: thread (row, half) owns columns
+        // [64*half, 64*half+64).  The MUFU pipe (16 ex2/clk/SM) and the conversion work are what bound a one-thread-per-row
+        // softmax; eight warps keep them busy while the UMMA pipe works on the next tile.  The two halves of a row exchange
+        // their maxima through shared memory once per tile (one named barrier), so both use the same reference max.
         const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int tok = tok0 + row / p.G;
@@ -228,27 +247,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
         float m_run = -INFINITY, l_run = 0.f;
-        // a warp none of whose 32 rows is a real query row (decode: 3 of the 4 warps) only keeps the barriers moving
-        const bool warp_active = __any_sync(0xffffffffu, valid);
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
-            const int kv0 = (my_begin + j) * BN;
+            const int kv0 = (my_begin + j) * BN + half * 64;
+            if (threadIdx.x == 64) ATRACE(0, j);
             mbar_wait(&bars->s_full[b], (j >> 1) & 1);
             tc_fence_after();
-            if (!warp_active) {
-                tc_fence_before();
-                mbar_arrive(&bars->p_full[b]);
-                continue;
-            }
-            uint32_t sr[4][32];
+            if (threadIdx.x == 64) ATRACE(1, j);
+            uint32_t sr[2][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + b * 128 + c * 32, sr[c]);
+            for (int c = 0; c < 2; ++c) tmem_ld32(tmem + lane_addr + b * 128 + half * 64 + c * 32, sr[c]);
             tmem_wait_ld();
-            const bool need_mask = (kv0 < lo) || (kv0 + BN > hi);
+            if (threadIdx.x == 64) ATRACE(2, j);
+            const bool need_mask = (kv0 < lo) || (kv0 + 64 > hi);
             float mt_raw = -INFINITY;                      // max of the RAW scores (scale > 0 keeps the order)
             if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int kv = kv0 + c * 32 + i;
@@ -258,64 +273,81 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) mt_raw = fmaxf(mt_raw, __uint_as_float(sr[c][i]));
                 }
             }
-            const float mt = mt_raw * p.scale_log2;
+            bars->xmax[b][half][row] = mt_raw;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) ATRACE(3, j);
+            const float mt = fmaxf(mt_raw, bars->xmax[b][half ^ 1][row]) * p.scale_log2;
             const bool upd = mt > m_run + RESCALE_THRESHOLD;      // also true for the first finite tile (m_run = -inf)
             const float m_new = upd ? mt : m_run;
             const float alpha = upd ? ex2_approx(m_run - m_new) : 1.0f; // m_run = -inf -> 0
             if (__any_sync(0xffffffffu, upd && j > 0)) {
-                // rescale the running O row; PV(j-1) must have landed first.  s_full(j) observed => PV(j-3) and
-                // everything older completed, so barrier (j-1)&1 is in one of exactly two states and the parity
-                // test is unambiguous even though earlier phases were never waited on.
+                // rescale this thread's half of the running O row; PV(j-1) must have landed first.  s_full(j) observed =>
+                // PV(j-3) and everything older completed, so barrier (j-1)&1 is in one of exactly two states and the
+                // parity test is unambiguous even though earlier phases were never waited on.
                 mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t orow[32];
-                    tmem_ld32(tmem + lane_addr + 256 + c * 32, orow);
+                    tmem_ld32(tmem + lane_addr + 256 + half * 64 + c * 32, orow);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
-                    tmem_st32(tmem + lane_addr + 256 + c * 32, orow);
+                    tmem_st32(tmem + lane_addr + 256 + half * 64 + c * 32, orow);
                 }
             }
             const float neg_m = (m_new == -INFINITY) ? 0.f : -m_new;
             float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, neg_m));
+                    // 7 of every 16 exponentials on the FMA pipe (ex2_poly), 9 on the MUFU pipe: the split that balances the
+                    // two pipes given the FFMA (scale) and FADD (row sum) every element also costs on the FMA pipe
+                    const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, neg_m);
+                    const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, neg_m);
+                    const float p0 = ((i & 7) == 7) ? ex2_approx(x0) : (((i & 1) == 0) ? ex2_approx(x0) : ex2_poly(x0));
+                    const float p1 = ((i & 1) == 0) ? ex2_poly(x1) : ex2_approx(x1);
                     lsum0 += p0;
                     lsum1 += p1;
+#ifdef SVLM_EXPERIMENT_TRUNC_PACK
+                    pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
+#else
                     pk[i] = pack_bf16(p0, p1);
+#endif
                 }
-                tmem_st16(tmem + lane_addr + b * 128 + c * 16, pk);
+                tmem_st16(tmem + lane_addr + b * 128 + half * 32 + c * 16, pk);
             }
             l_run = l_run * alpha + (lsum0 + lsum1);
             m_run = m_new;
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bars->p_full[b]);
+            if (threadIdx.x == 64) ATRACE(4, j);
         }
 
-        // ---- epilogue ----
+        // ---- epilogue: the two halves add their row sums, each stores its 64 output columns ----
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // every thread is past its last xmax read
+        bars->xmax[0][half][row] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l_tot = bars->xmax[0][0][row] + bars->xmax[0][1][row];
         if (n_tiles > 0) {
             mbar_wait(&bars->o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
             tc_fence_after();
         }
         const int hq = head * p.G + g;
-        const float inv = (p.num_splits == 1) ? (l_run > 0.f ? 1.0f / l_run : 0.f) : 1.0f;
+        const float inv = (p.num_splits == 1) ? (l_tot > 0.f ? 1.0f / l_tot : 0.f) : 1.0f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;       // 32-column chunk of the output row
             uint32_t orow[32];
-            if (n_tiles > 0 && warp_active) {
+            if (n_tiles > 0) {
                 tmem_ld32(tmem + lane_addr + 256 + c * 32, orow);
                 tmem_wait_ld();
             } else {
@@ -346,7 +378,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
         }
-        if (valid && p.num_splits > 1) p.part_ml[((int64_t)split * p.Tq + tok) * p.Hq + hq] = make_float2(m_run, l_run);
+        if (valid && half == 0 && p.num_splits > 1) p.part_ml[((int64_t)split * p.Tq + tok) * p.Hq + hq] = make_float2(m_run, l_tot);
     }
 
     tc_fence_before();
@@ -478,6 +510,9 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
     p.part_o = (float*)workspace;
     p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + rows * D) : nullptr;
     p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef SVLM_TRACE
+    { const char* v = getenv("SVLM_TRACE_PTR"); p.trace = v ? (unsigned long long*)strtoull(v, nullptr, 0) : nullptr; }
+#endif
     dim3 grid((n_q_tokens + tpt - 1) / tpt, H, num_splits);
     if ((rc = launch_attn(MODE_CAUSAL, tq, tk, tv, p, grid, (cudaStream_t)stream))) return rc;
     if (num_splits > 1) {

@@ -78,6 +78,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + r, |r| <= 0.5, degree-3 minimax polynomial for 2^r
+// (relative error 7.5e-5, far below bf16's 2^-9), exponent patched in with an integer shift-add.  Valid for x <= ~100;
+// x < -125 (incl. -inf) returns ~2^-125.  B200's MUFU pipe and its FMA pipe each bound a softmax that uses only one of
+// them (measured: ~16 and ~2 cycles per warp instruction per SM sub-partition); evaluating a fixed share of the
+// exponentials here lets the two pipes run side by side (the FlashAttention-4 idea).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                       // 1.5 * 2^23: low mantissa bits = round(x)
+    const float r = x - (t - 12582912.0f);
+    float p = fmaf(5.517165e-2f, r, 2.426111e-1f);
+    p = fmaf(p, r, 6.932610e-1f);
+    p = fmaf(p, r, 9.999281e-1f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
@@ -120,6 +134,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef SVLM_EXPERIMENT_SLEEP
+        __nanosleep(SVLM_EXPERIMENT_SLEEP);
+#endif
         if (++spins > (1u << 24)) {
             printf("svlm: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
