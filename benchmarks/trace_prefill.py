@@ -28,6 +28,7 @@ tt = t[0, 1, 3]
 nt = int((tt[:, 1] > 0).sum())
 base = int(tt[0, 0])
 ev = ["top", "s_seen", "ld", "bar_issue", "arrived"]
-for j in range(4, min(nt, 9)):
+for j in range(6, min(nt, 8)):
     for name, o in (("w2 smsp2 half0", 0), ("w6 smsp2 half1", 5), ("w4 smsp0 half0", 10)):
         print(j, name, " ".join(f"{ev[e]}={int(tt[j, o + e]) - base:6d}" for e in range(5)))
+print("cycles/tile:", (int(tt[nt - 1, 4]) - int(tt[1, 4])) / (nt - 2))

@@ -302,28 +302,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
             const float neg_m = (m_new == -INFINITY) ? 0.f : -m_new;
-            float lsum0 = 0.f, lsum1 = 0.f;
+            // p = 2^(s * scale - m) on PAIRS of columns with packed fp32x2 math (one FFMA2 for the scale, one FADD2 for the row
+            // sum, one F2FP for the bf16 pack per pair).  7 of 16 pairs take the polynomial on the FMA pipe, 9 the MUFU pipe:
+            // the split that balances the two pipes (issue-slot count, not MUFU alone, bounds this loop on B200).
+            const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
+            uint64_t lsum2 = pack2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    // 7 of every 16 exponentials on the FMA pipe (ex2_poly), 9 on the MUFU pipe: the split that balances the
-                    // two pipes given the FFMA (scale) and FADD (row sum) every element also costs on the FMA pipe
-                    const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, neg_m);
-                    const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, neg_m);
-                    const float p0 = ((i & 7) == 7) ? ex2_approx(x0) : (((i & 1) == 0) ? ex2_approx(x0) : ex2_poly(x0));
-                    const float p1 = ((i & 1) == 0) ? ex2_poly(x1) : ex2_approx(x1);
-                    lsum0 += p0;
-                    lsum1 += p1;
-#ifdef SVLM_EXPERIMENT_TRUNC_PACK
-                    pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
-#else
-                    pk[i] = pack_bf16(p0, p1);
-#endif
+                    const uint64_t x = ffma2((uint64_t)sr[c][2 * i] | ((uint64_t)sr[c][2 * i + 1] << 32), scale2, negm2);
+                    const uint64_t pp = ((i & 1) && i != 15) ? ex2_poly2(x) : pack2(ex2_approx(lo2(x)), ex2_approx(hi2(x)));
+                    lsum2 = fadd2(lsum2, pp);
+                    pk[i] = pack_bf16(lo2(pp), hi2(pp));
                 }
                 tmem_st16(tmem + lane_addr + b * 128 + half * 32 + c * 16, pk);
             }
+            const float lsum0 = lo2(lsum2), lsum1 = hi2(lsum2);
             l_run = l_run * alpha + (lsum0 + lsum1);
             m_run = m_new;
             tmem_wait_st();

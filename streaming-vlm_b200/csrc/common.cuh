@@ -92,6 +92,40 @@ __device__ __forceinline__ float ex2_poly(float x) {
     p = fmaf(p, r, 9.999281e-1f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue one instruction for two fp32 lanes of a 64-bit register pair)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo2(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// ex2_poly on two lanes at once: 6 FMA-pipe instructions per pair (2 FADD2 + 4 FFMA2) + 2 clamps and 2 shift-adds on the ALU pipe
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x) {
+    x = pack2(fmaxf(lo2(x), -125.0f), fmaxf(hi2(x), -125.0f));
+    const uint64_t t = fadd2(x, pack2(12582912.0f, 12582912.0f));
+    const uint64_t u = fadd2(t, pack2(-12582912.0f, -12582912.0f));
+    const uint64_t r = ffma2(u, pack2(-1.0f, -1.0f), x);
+    uint64_t q = ffma2(pack2(5.517165e-2f, 5.517165e-2f), r, pack2(2.426111e-1f, 2.426111e-1f));
+    q = ffma2(q, r, pack2(6.932610e-1f, 6.932610e-1f));
+    q = ffma2(q, r, pack2(9.999281e-1f, 9.999281e-1f));
+    const uint32_t a = (uint32_t)q + ((uint32_t)t << 23);
+    const uint32_t b = (uint32_t)(q >> 32) + ((uint32_t)(t >> 32) << 23);
+    return (uint64_t)a | ((uint64_t)b << 32);
+}
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
@@ -134,9 +168,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-#ifdef SVLM_EXPERIMENT_SLEEP
-        __nanosleep(SVLM_EXPERIMENT_SLEEP);
-#endif
         if (++spins > (1u << 24)) {
             printf("svlm: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, smem_u32(bar), parity);
