@@ -185,6 +185,13 @@ int svlm_swiglu(const void* gate_up, void* out, int rows, int M, int64_t gate_up
  * ------------------------------------------------------------------------------------- */
 int svlm_gemv_bf16(const void* W, const void* x, const void* norm_weight, float eps, const void* bias,
                    const void* residual, void* y, int N, int K, int mode, void* stream);
+/* Decode-step fusion of (7, mode 0 on the fused [q;k;v] weight) with (3): RMSNorm + QKV projection + bias, then the rows of
+ * each head are rotated (text position *pos_dev on all three mRoPE axes) and written straight to q_rot [Hq][128] and to
+ * the arena row *row_dev (K_raw, K_rot, V) of `layer` -- no intermediate qkv vector, no separate append launch. */
+int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, const void* W, const void* x,
+                              const void* norm_weight, float eps, const void* bias, int q_heads, int hidden, void* q_rot,
+                              const int32_t* row_dev, const int32_t* pos_dev, const void* cos_table, const void* sin_table,
+                              int table_rows, void* stream);
 int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
                         int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
                         int32_t* next_pos, void* stream);

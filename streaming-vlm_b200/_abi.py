@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
 
@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_swiglu.argtypes = [vp, vp, c_int, c_int, c_int64, c_int64, vp]
     L.svlm_gemv_bf16.argtypes = [vp, vp, vp, c_float, vp, vp, vp, c_int, c_int, c_int, vp]
+    L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
     for name in EXPORTS:
@@ -203,6 +204,15 @@ def gemv_bf16(w, x, y, mode: int = 0, norm_weight=None, eps: float = 1e-6, bias=
     n = y.numel()
     check(lib().svlm_gemv_bf16(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(bias), _ptr(residual), y.data_ptr(), n,
                                w.shape[1], mode, _stream()), "svlm_gemv_bf16")
+
+
+def gemv_qkv_rope_append(arena: ArenaView, buffer: int, layer: int, w, x, norm_weight, eps, bias, q_heads: int, q_rot, row_dev, pos_dev,
+                         cos_table, sin_table):
+    _req_cuda(w, x, q_rot, row_dev, pos_dev)
+    check(lib().svlm_gemv_qkv_rope_append(arena.ref, buffer, layer, w.data_ptr(), x.data_ptr(), norm_weight.data_ptr(), eps, _ptr(bias),
+                                          q_heads, w.shape[1], q_rot.data_ptr(), row_dev.data_ptr(), pos_dev.data_ptr(),
+                                          cos_table.data_ptr(), sin_table.data_ptr(), cos_table.shape[0], _stream()),
+          "svlm_gemv_qkv_rope_append")
 
 
 def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, kv_len, kv_after, next_pos):

@@ -15,7 +15,7 @@
 namespace svlm {
 
 constexpr int GEMV_THREADS = 256;
-enum { GEMV_PLAIN = 0, GEMV_RESID = 1, GEMV_SWIGLU = 2, GEMV_ARGMAX = 3 };
+enum { GEMV_PLAIN = 0, GEMV_RESID = 1, GEMV_SWIGLU = 2, GEMV_ARGMAX = 3, GEMV_QKV = 4 };
 
 struct GemvParams {
     const uint16_t* W;
@@ -28,6 +28,18 @@ struct GemvParams {
     int N, K;                   // N = number of outputs (SWIGLU: W has 2N rows)
     const uint8_t* suppress;    // ARGMAX: 1 = never emit
     unsigned long long* key;    // ARGMAX: packed (ordered logit << 32 | ~index), reduced with atomicMax
+    // QKV: rotate + append epilogue (decode step: one token, plain-text position on all three mRoPE axes)
+    uint16_t* q_rot;            // bf16 [Hq][128]
+    uint16_t* arena_buf;        // base of the live arena buffer (plane 0)
+    int64_t plane_elems;        // elements per plane
+    int64_t head_stride;        // elements per (layer, head) = cap * 128
+    int layer_head_base;        // layer * Hkv
+    int hq, hkv, cap;
+    const int32_t* row_dev;     // arena row of the new token
+    const int32_t* pos_dev;     // its position
+    const uint16_t* cos_tab;    // bf16 [rows][64]
+    const uint16_t* sin_tab;
+    int tab_rows;
 };
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
@@ -99,11 +111,19 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
     const int grp = warp / KS, ks = warp % KS;
     const int n0 = (blockIdx.x * GROUPS + grp) * RG;
     const uint16_t* rows[NR];
+    if (MODE == GEMV_QKV) {
+        // group index -> (head, j): rows head*128 + j and head*128 + 64 + j, the two halves mRoPE mixes
+        const int gidx = min(blockIdx.x * GROUPS + grp, p.N / 2 - 1);
+        const int n = (gidx >> 6) * 128 + (gidx & 63);
+        rows[0] = p.W + (int64_t)n * K;
+        rows[NR - 1] = p.W + (int64_t)(n + 64) * K;
+    } else {
 #pragma unroll
-    for (int r = 0; r < RG; ++r) {
-        const int n = min(n0 + r, p.N - 1);
-        rows[r] = p.W + (int64_t)n * K;
-        if (MODE == GEMV_SWIGLU) rows[RG + r] = p.W + (int64_t)(p.N + n) * K;
+        for (int r = 0; r < RG; ++r) {
+            const int n = min(n0 + r, p.N - 1);
+            rows[r] = p.W + (int64_t)n * K;
+            if (MODE == GEMV_SWIGLU) rows[RG + r] = p.W + (int64_t)(p.N + n) * K;
+        }
     }
     float acc[NR];
 #pragma unroll
@@ -137,6 +157,50 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
         for (int r = 0; r < NR; ++r) part[warp][r] = acc[r];
     }
     __syncthreads();
+
+    if (MODE == GEMV_QKV) {
+        // thread g < GROUPS finishes both rows of group g: bias, bf16 rounding (the Linear's output), then the reference's
+        // mRoPE rounding order out = bf16(bf16(x*cos) + bf16(rot(x)*sin)); q -> q_rot, k -> K_raw + K_rot, v -> V (arena row *row_dev)
+        const int g = threadIdx.x;
+        const int gidx = blockIdx.x * GROUPS + g;
+        if (g < GROUPS && gidx < p.N / 2) {
+            float lo = 0.f, hi = 0.f;
+#pragma unroll
+            for (int k2 = 0; k2 < KS; ++k2) { lo += part[g * KS + k2][0]; hi += part[g * KS + k2][1]; }
+            const int head = gidx >> 6, j = gidx & 63, n = head * 128 + j;
+            if (p.bias) {
+                lo += __bfloat162float(__ushort_as_bfloat16(p.bias[n]));
+                hi += __bfloat162float(__ushort_as_bfloat16(p.bias[n + 64]));
+            }
+            lo = round_bf16(lo);
+            hi = round_bf16(hi);
+            const uint16_t lo_b = __bfloat16_as_ushort(__float2bfloat16_rn(lo)), hi_b = __bfloat16_as_ushort(__float2bfloat16_rn(hi));
+            if (head < p.hq + p.hkv) {
+                const int pos = min(max(__ldg(p.pos_dev), 0), p.tab_rows - 1);
+                const float c = __bfloat162float(__ushort_as_bfloat16(p.cos_tab[(int64_t)pos * 64 + j]));
+                const float sn = __bfloat162float(__ushort_as_bfloat16(p.sin_tab[(int64_t)pos * 64 + j]));
+                const uint16_t rlo = __bfloat16_as_ushort(__float2bfloat16_rn(__fadd_rn(round_bf16(__fmul_rn(lo, c)), round_bf16(__fmul_rn(-hi, sn)))));
+                const uint16_t rhi = __bfloat16_as_ushort(__float2bfloat16_rn(__fadd_rn(round_bf16(__fmul_rn(hi, c)), round_bf16(__fmul_rn(lo, sn)))));
+                if (head < p.hq) {
+                    p.q_rot[head * 128 + j] = rlo;
+                    p.q_rot[head * 128 + 64 + j] = rhi;
+                } else {
+                    const int row = min(__ldg(p.row_dev), p.cap - 1);
+                    const int64_t o = (int64_t)(p.layer_head_base + head - p.hq) * p.head_stride + (int64_t)row * 128 + j;
+                    p.arena_buf[o] = lo_b;                                   // plane 0: K_raw
+                    p.arena_buf[o + 64] = hi_b;
+                    p.arena_buf[p.plane_elems + o] = rlo;                    // plane 1: K_rot
+                    p.arena_buf[p.plane_elems + o + 64] = rhi;
+                }
+            } else {
+                const int row = min(__ldg(p.row_dev), p.cap - 1);
+                const int64_t o = 2 * p.plane_elems + (int64_t)(p.layer_head_base + head - p.hq - p.hkv) * p.head_stride + (int64_t)row * 128 + j;
+                p.arena_buf[o] = lo_b;                                       // plane 2: V
+                p.arena_buf[o + 64] = hi_b;
+            }
+        }
+        return;
+    }
 
     // ---- epilogue: thread t finishes output row (group t / RG, row t % RG)
     const int t = threadIdx.x;
@@ -203,7 +267,7 @@ static int launch_gemv(const GemvParams& p, cudaStream_t st) {
         attr_done = true;
     }
     const int rows_per_cta = (8 / KS) * RG;
-    const int grid = (p.N + rows_per_cta - 1) / rows_per_cta;
+    const int grid = (p.N + rows_per_cta - 1) / rows_per_cta;      // QKV: RG = 2 -> one group per (n, n+64) pair, same count
     gemv_kernel<MODE, RG, KS, U, STAGE><<<grid, GEMV_THREADS, smem, st>>>(p);
     return launch_status("gemv_kernel");
 }
@@ -266,4 +330,32 @@ extern "C" int svlm_lm_head_argmax(const void* W, const void* x, const void* nor
     if ((rc = dispatch_rw<GEMV_ARGMAX>(p, (cudaStream_t)stream))) return rc;
     decode_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
     return launch_status("decode_finalize_kernel");
+}
+
+extern "C" int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, const void* W, const void* x,
+                                         const void* norm_weight, float eps, const void* bias, int q_heads, int hidden, void* q_rot,
+                                         const int32_t* row_dev, const int32_t* pos_dev, const void* cos_table, const void* sin_table,
+                                         int table_rows, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    if ((rc = validate_arena(arena))) return rc;
+    SVLM_REQUIRE(buffer == 0 || buffer == 1, "buffer must be 0 or 1");
+    SVLM_REQUIRE(layer >= 0 && layer < arena->layers, "layer %d out of range", layer);
+    SVLM_REQUIRE(norm_weight && q_rot && row_dev && pos_dev && cos_table && sin_table, "NULL argument");
+    SVLM_REQUIRE(q_heads > 0 && table_rows > 0, "bad q_heads / table_rows");
+    const int N = (q_heads + 2 * arena->kv_heads) * 128;
+    if ((rc = gemv_common_checks(W, x, q_rot, N, hidden))) return rc;
+    ArenaDims ad{arena->layers, arena->kv_heads, arena->head_dim, arena->capacity};
+    GemvParams p{};
+    p.W = (const uint16_t*)W; p.x = (const uint16_t*)x; p.norm_w = (const uint16_t*)norm_weight; p.eps = eps;
+    p.bias = (const uint16_t*)bias; p.N = N; p.K = hidden;
+    p.q_rot = (uint16_t*)q_rot;
+    p.arena_buf = (uint16_t*)arena->base + (int64_t)buffer * ad.buffer_elems();
+    p.plane_elems = ad.plane_elems();
+    p.head_stride = (int64_t)ad.cap * ad.D;
+    p.layer_head_base = layer * arena->kv_heads;
+    p.hq = q_heads; p.hkv = arena->kv_heads; p.cap = arena->capacity;
+    p.row_dev = row_dev; p.pos_dev = pos_dev;
+    p.cos_tab = (const uint16_t*)cos_table; p.sin_tab = (const uint16_t*)sin_table; p.tab_rows = table_rows;
+    return launch_gemv<GEMV_QKV, 2, 2, 4, true>(p, (cudaStream_t)stream);
 }

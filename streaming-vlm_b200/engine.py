@@ -369,19 +369,16 @@ class StreamingEngine:
         c, g = self.cache, self.geo
         hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
         x = F.embedding(self.tok_dev, self.embed)[0].contiguous()
-        qkv, q_rot, o, act = self._dec_qkv, self._dec_q, self._dec_o, self._dec_act
-        q2 = qkv.view(1, -1)
-        q, k, v = q2[:, :hq * d], q2[:, hq * d:(hq + hkv) * d], q2[:, (hq + hkv) * d:]
+        q_rot, o, act = self._dec_q, self._dec_o, self._dec_act
         for li, L in enumerate(self.layers):
-            _abi.gemv_bf16(L["wqkv"], x, qkv, 0, L["ln1"], g.rms_eps, L["bqkv"])
-            _abi.qkv_rope_append(c.view, c.cur, li, q, k, v, 1, hq, q_rot, 0, None, c.cos_table, c.sin_table, c.section,
-                                 start_dev=self.kv_len_dev, text_pos_dev=c.next_pos)
-            _abi.attn_causal(c.view, c.cur, li, q_rot, o, 1, hq, c.capacity, self.scale, self.decode_splits,
-                             self.ws if self.decode_splits > 1 else None, kv_len_dev=self.kv_after_dev)
+            _abi.gemv_qkv_rope_append(c.view, c.cur, li, L["wqkv"], x, L["ln1"], g.rms_eps, L["bqkv"], hq, q_rot, self.kv_len_dev,
+                                      c.next_pos, c.cos_table, c.sin_table)
+            _abi.attn_causal(c.view, c.cur, li, q_rot, o, 1, hq, c.capacity, self.scale, self._splits_now,
+                             self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev)
             _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
             _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
             _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
-        self.launches += g.num_layers * (6 + (1 if self.decode_splits > 1 else 0))
+        self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0))
         _abi.lm_head_argmax(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
                             self.kv_len_dev, self.kv_after_dev, c.next_pos)
         self.launches += 2
@@ -391,8 +388,12 @@ class StreamingEngine:
         c = self.cache
         if c.seq_len + 1 > c.capacity:
             raise RuntimeError(f"arena capacity {c.capacity} exceeded during decode")
+        # split count for the current cache length: ~3 key tiles per CTA keeps the serial TMA->UMMA->softmax chain short
+        # without drowning the merge kernel in partials (swept in benchmarks/microbench.py); capped by the workspace
+        n_tiles = (c.seq_len + 128) // 128
+        self._splits_now = max(1, min(self.decode_splits, -(-n_tiles // 3)))
         if self.use_graph:
-            gr = self._graphs.get(c.cur)
+            gr = self._graphs.get((c.cur, self._splits_now))
             if gr is None:
                 # warm up once outside capture (cuBLAS workspaces, lazy kernel loading), then restore the state it advanced
                 saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone(), self.kv_after_dev.clone())
@@ -409,7 +410,7 @@ class StreamingEngine:
                     self._decode_body()
                 self._graph_launches = self.launches - before
                 self.launches = before
-                self._graphs[c.cur] = gr
+                self._graphs[(c.cur, self._splits_now)] = gr
             gr.replay()
             self.launches += self._graph_launches
         else:

@@ -372,3 +372,29 @@ def test_add_rmsnorm_and_swiglu(abi):
         abi.swiglu(gu.to(DEV), out)
         ref = torch.nn.functional.silu(gu[:, :m]) * gu[:, m:]
         torch.testing.assert_close(out.cpu().float(), ref.float(), rtol=1.6e-2, atol=1e-3)
+
+
+def test_gemv_qkv_rope_append_matches_unfused(abi, tables):
+    """Fused decode QKV projection + mRoPE + arena append == GEMV followed by svlm_qkv_rope_append, bit for bit."""
+    L, H, cap, Hq, hidden = 2, 4, 512, 28, 3584
+    g = torch.Generator().manual_seed(21)
+    w = (torch.randn((Hq + 2 * H) * 128, hidden, generator=g) / math.sqrt(hidden)).to(torch.bfloat16).to(DEV)
+    b = (torch.randn((Hq + 2 * H) * 128, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    x = torch.randn(hidden, generator=g).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(torch.bfloat16).to(DEV)
+    cos, sin = (t.to(DEV) for t in tables)
+    row = torch.tensor([77], dtype=torch.int32, device=DEV)
+    pos = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    _, a1, v1 = make_arena(abi, L, H, cap, seed=3)
+    _, a2, v2 = make_arena(abi, L, H, cap, seed=3)
+    qkv = torch.zeros((Hq + 2 * H) * 128, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_bf16(w, x, qkv, 0, nw, 1e-6, b)
+    q2 = qkv.view(1, -1)
+    q_ref = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    abi.qkv_rope_append(v1, 0, 1, q2[:, :Hq * 128], q2[:, Hq * 128:(Hq + H) * 128], q2[:, (Hq + H) * 128:], 1, Hq, q_ref, 0, None, cos, sin,
+                        SECTION, start_dev=row, text_pos_dev=pos)
+    q_fused = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_qkv_rope_append(v2, 0, 1, w, x, nw, 1e-6, b, Hq, q_fused, row, pos, cos, sin)
+    torch.cuda.synchronize()
+    assert torch.equal(bits(q_fused.cpu()), bits(q_ref.cpu()))
+    assert torch.equal(bits(a2.cpu()), bits(a1.cpu()))
