@@ -201,10 +201,11 @@ def kernel_rooflines(engine, pk):
     q1 = torch.randn(1, hq, d, device=dev).to(torch.bfloat16)
     o1 = torch.empty_like(q1)
     engine.kv_after_dev.fill_(n)
+    dsplits = getattr(engine, "_splits_now", engine.decode_splits)
 
     def dec():
         for li in range(L):
-            _abi.attn_causal(c.view, c.cur, li, q1, o1, 1, hq, c.capacity, engine.scale, engine.decode_splits, engine.ws,
+            _abi.attn_causal(c.view, c.cur, li, q1, o1, 1, hq, c.capacity, engine.scale, dsplits, engine.ws,
                              kv_len_dev=engine.kv_after_dev)
     t = timed(dec) / L
     byt = n * 2 * g.num_kv_heads * d * 2
@@ -270,9 +271,13 @@ def kernel_rooflines(engine, pk):
                        for _ in range(4)]) / 4
     out["gemv_norm_lm_head_argmax"] = {"bound": "hbm", "achieved": engine.lm_head.numel() * 2 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "us_per_launch": t * 1e6, "launches_per_step": NEW_TOKENS - 1, "weight_bytes": engine.lm_head.numel() * 2}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        traffic = {}
     for k, v in out.items():
         v["frac"] = v["achieved"] / v["peak"]
-        v["traffic"] = None
+        v["traffic"] = traffic.get(k)          # DRAM bytes per launch from the committed ncu --set full capture (or null)
         v["share_ms_per_step"] = v["us_per_launch"] * v["launches_per_step"] * 1e-3
     return out
 

@@ -429,6 +429,32 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
     out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
 }
 
+// Merge for FEW splits and MANY rows (chunk prefill: 2-4 splits x Tq*Hq rows): one thread per (row, 4 columns), fully
+// vectorised; the one-CTA-per-row kernel above would launch 8400 tiny CTAs here (measured 21 us vs ~3 us of traffic).
+__global__ void __launch_bounds__(256) attn_combine_rows_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                                                 uint16_t* __restrict__ out, int rows, int D, int num_splits) {
+    const int vec_per_row = D / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)rows * vec_per_row) return;
+    const int r = (int)(idx / vec_per_row), c = (int)(idx % vec_per_row) * 4;
+    float M = -INFINITY;
+    for (int s = 0; s < num_splits; ++s) M = fmaxf(M, part_ml[(int64_t)s * rows + r].x);
+    float L = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < num_splits; ++s) {
+        const float2 ml = part_ml[(int64_t)s * rows + r];
+        const float w = (ml.x == -INFINITY) ? 0.f : ex2_approx(ml.x - M);
+        const float4 v = *reinterpret_cast<const float4*>(part_o + ((int64_t)s * rows + r) * D + c);
+        L += w * ml.y;
+        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+    const float inv = L > 0.f ? 1.0f / L : 0.f;
+    uint2 o;
+    o.x = pack_bf16(acc.x * inv, acc.y * inv);
+    o.y = pack_bf16(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(out + (int64_t)r * D + c) = o;
+}
+
 static int launch_attn(int mode, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t st) {
     static bool attr_done[2] = {false, false};
@@ -512,7 +538,14 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
     dim3 grid((n_q_tokens + tpt - 1) / tpt, H, num_splits);
     if ((rc = launch_attn(MODE_CAUSAL, tq, tk, tv, p, grid, (cudaStream_t)stream))) return rc;
     if (num_splits > 1) {
-        attn_combine_kernel<<<n_q_tokens * q_heads, 128, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, n_q_tokens * q_heads, D, num_splits);
+        const int rows = n_q_tokens * q_heads;
+        if (num_splits <= 8 && rows >= 256) {
+            const int64_t threads = (int64_t)rows * (D / 4);
+            attn_combine_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, rows, D,
+                                                                                                     num_splits);
+        } else {
+            attn_combine_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, rows, D, num_splits);
+        }
         return launch_status("attn_combine_kernel");
     }
     return SVLM_OK;
