@@ -39,6 +39,16 @@ def bits(t):
     return t.contiguous().view(torch.int16)
 
 
+def cos_sin_at(tables, pos_int):
+    """cos/sin [3,1,n,128] for integer positions [3,n], gathered from the SAME host-built table the kernels index (HF's
+    `emb = cat(freqs, freqs)` duplicates the 64 frequencies).  Recomputing cos() here instead could differ from the table in
+    the last fp32 bit (vectorised vs scalar libm path) and flip a bf16 rounding once in ~1e5 values."""
+    tc, ts = tables
+    idx = pos_int.long()
+    c, s_ = tc[idx], ts[idx]                                   # [3, n, 64]
+    return torch.cat((c, c), dim=-1)[:, None], torch.cat((s_, s_), dim=-1)[:, None]
+
+
 def make_arena(abi, L, H, cap, seed=0, fill=True):
     g = torch.Generator().manual_seed(seed)
     a = torch.zeros(2, 3, L, H, cap, 128, dtype=torch.bfloat16)
@@ -131,12 +141,12 @@ def test_mrope_positions_long_and_edge(abi):
 
 
 # ------------------------------------------------------------------------------------------------ compaction + RoPE
-def _oracle_compact(arena_cpu, gather, pos_f32, tables):
+def _oracle_compact(arena_cpu, gather, pos_int, tables):
     """new K_raw / V = gather; K_rot = reference mRoPE of the gathered raw keys."""
     idx = torch.tensor(gather, dtype=torch.long)
     k_raw = arena_cpu[0, 0].index_select(2, idx)        # [L,H,n,D]
     v = arena_cpu[0, 2].index_select(2, idx)
-    cos, sin = o_pos.rotary_cos_sin(pos_f32, o_pos.default_inv_freq(128, 1e6))
+    cos, sin = cos_sin_at(tables, pos_int)
     L, H, n, D = k_raw.shape
     _, k_rot = o_pos.apply_mrope(k_raw.reshape(1, L * H, n, D)[:, :1, :1], k_raw.reshape(1, L * H, n, D), cos, sin, SECTION)
     return k_raw, k_rot.reshape(L, H, n, D), v
@@ -165,7 +175,7 @@ def test_kv_compact_rope_bit_exact(abi, tables, golden_dir, stream_idx, round_id
     abi.kv_compact_rope(view, 0, runs, pos_dev, cos.to(DEV), sin.to(DEV), SECTION)
     torch.cuda.synchronize()
     got = arena_dev.cpu()
-    k_raw, k_rot, v = _oracle_compact(arena_cpu, gather, pos_i[:, None, :n].float(), tables)
+    k_raw, k_rot, v = _oracle_compact(arena_cpu, gather, pos_i[:, :n], tables)
     assert torch.equal(bits(got[1, 0, :, :, :n]), bits(k_raw))
     assert torch.equal(bits(got[1, 2, :, :, :n]), bits(v))
     assert torch.equal(bits(got[1, 1, :, :, :n]), bits(k_rot))
@@ -199,8 +209,7 @@ def test_qkv_rope_append_bit_exact(abi, tables):
     q_out = torch.zeros(T, Hq, 128, dtype=torch.bfloat16, device=DEV)
     abi.qkv_rope_append(view, 1, 1, q, k, v, T, Hq, q_out, start, pos_i.to(DEV), cos.to(DEV), sin.to(DEV), SECTION)
     torch.cuda.synchronize()
-    pf = pos_i[:, None, start:start + T].float()
-    c, s = o_pos.rotary_cos_sin(pf, o_pos.default_inv_freq(128, 1e6))
+    c, s = cos_sin_at(tables, pos_i[:, start:start + T])
     q_ref, k_ref = o_pos.apply_mrope(qkv[:, :Hq * 128].view(1, T, Hq, 128).transpose(1, 2),
                                      qkv[:, Hq * 128:(Hq + H) * 128].view(1, T, H, 128).transpose(1, 2), c, s, SECTION)
     got = arena_dev.cpu()
@@ -217,8 +226,7 @@ def test_qkv_rope_append_bit_exact(abi, tables):
     q1 = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
     abi.qkv_rope_append(view, 1, 0, q[:1], k[:1], v[:1], 1, Hq, q1, 0, None, cos.to(DEV), sin.to(DEV), SECTION,
                         start_dev=start_dev, text_pos_dev=tpos)
-    pf = torch.full((3, 1, 1), 1234.0)
-    c, s = o_pos.rotary_cos_sin(pf, o_pos.default_inv_freq(128, 1e6))
+    c, s = cos_sin_at(tables, torch.full((3, 1), 1234))
     q_ref, k_ref = o_pos.apply_mrope(qkv[:1, :Hq * 128].view(1, 1, Hq, 128).transpose(1, 2),
                                      qkv[:1, Hq * 128:(Hq + H) * 128].view(1, 1, H, 128).transpose(1, 2), c, s, SECTION)
     assert torch.equal(bits(q1.cpu()), bits(q_ref[0].transpose(0, 1)))

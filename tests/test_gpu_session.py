@@ -57,7 +57,11 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
             assert np.array_equal(pos_got, pos_ref[:, :n]), f"chunk {i}: positions"
             # K_rot == reference mRoPE applied to the arena's own K_raw at those positions (bit-exact)
             k_raw, k_rot, _ = engine.cache.planes(0)
-            cos, sin = o_pos.rotary_cos_sin(taps_o["position_ids"][:, :, :n], o_pos.default_inv_freq(128, 1e6))
+            # cos/sin gathered from the engine's own host-built table (same arithmetic as HF's rotary module, see
+            # tests/test_oracle_golden.py::test_rotary_table_equals_per_position_embedding) at the ORACLE's positions
+            idx = taps_o["position_ids"][:, 0, :n].long()
+            tc, ts = engine.cache.cos_table.cpu()[idx], engine.cache.sin_table.cpu()[idx]
+            cos, sin = torch.cat((tc, tc), dim=-1)[:, None], torch.cat((ts, ts), dim=-1)[:, None]
             kr = k_raw[:, :n].cpu()
             _, ref_rot = o_pos.apply_mrope(kr[None, :1, :1], kr[None], cos, sin, geo.mrope_section)
             assert torch.equal(k_rot[:, :n].cpu().view(torch.int16), ref_rot[0].view(torch.int16)), f"chunk {i}: K_rot"
