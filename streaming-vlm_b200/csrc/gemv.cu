@@ -273,15 +273,48 @@ static int launch_gemv(const GemvParams& p, cudaStream_t st) {
 }
 
 // Shape heuristics (B200, 148 SMs): enough CTAs x bytes in flight to cover the HBM latency-bandwidth product.
-//   long rows (K >= 8192, the MLP down projection): 8 warps split K for 4 rows
-//   few rows  (N < 16384: q/k/v, o):                2 warps split K for 2 rows, 4 k-steps in flight
+//   long rows (K >= 8192, the MLP down projection): 4 warps split K for 2 rows (2 row groups per CTA)
+//   few rows  (N < 16384: o_proj, plain q/k/v):     4 warps split K for 4 rows, 4 k-steps in flight
 //   many rows (gate/up, lm_head):                   one warp owns its rows
+#ifdef SVLM_TUNE
+// developer build only: pick the (RG, KS, U) configuration from the environment to sweep it (benchmarks/gemv_tune.py)
+#include <stdlib.h>
+template <int MODE, bool STAGE>
+static int dispatch_tune(const GemvParams& p, cudaStream_t st, const char* var) {
+    const char* v = getenv(var);
+    const int c = v ? atoi(v) : -1;
+    switch (c) {
+        case 0: return launch_gemv<MODE, 4, 8, 2, STAGE>(p, st);
+        case 1: return launch_gemv<MODE, 2, 8, 4, STAGE>(p, st);
+        case 2: return launch_gemv<MODE, 2, 8, 2, STAGE>(p, st);
+        case 3: return launch_gemv<MODE, 4, 4, 2, STAGE>(p, st);
+        case 4: return launch_gemv<MODE, 4, 4, 4, STAGE>(p, st);
+        case 5: return launch_gemv<MODE, 2, 4, 4, STAGE>(p, st);
+        case 6: return launch_gemv<MODE, 2, 2, 4, STAGE>(p, st);
+        case 7: return launch_gemv<MODE, 1, 2, 4, STAGE>(p, st);
+        case 8: return launch_gemv<MODE, 1, 4, 4, STAGE>(p, st);
+        case 9: return launch_gemv<MODE, 2, 4, 2, STAGE>(p, st);
+        case 10: return launch_gemv<MODE, 4, 2, 2, STAGE>(p, st);
+        case 11: return launch_gemv<MODE, 1, 8, 4, STAGE>(p, st);
+        case 12: return launch_gemv<MODE, 2, 1, 4, STAGE>(p, st);
+        case 13: return launch_gemv<MODE, 1, 1, 8, STAGE>(p, st);
+        default: return -100;
+    }
+}
+#endif
+
 template <int MODE, bool STAGE>
 static int dispatch_shape(const GemvParams& p, cudaStream_t st) {
+#ifdef SVLM_TUNE
+    if (MODE == GEMV_PLAIN || MODE == GEMV_RESID) {
+        const int rc = dispatch_tune<MODE, STAGE>(p, st, p.K >= 8192 ? "SVLM_TUNE_LONGK" : "SVLM_TUNE_FEWROWS");
+        if (rc != -100) return rc;
+    }
+#endif
     if (MODE == GEMV_SWIGLU) return launch_gemv<MODE, 2, 1, 2, STAGE>(p, st);
     if (MODE == GEMV_ARGMAX) return launch_gemv<MODE, 4, 1, 2, STAGE>(p, st);
-    if (p.K >= 8192) return launch_gemv<MODE, 4, 8, 2, STAGE>(p, st);
-    if (p.N < 16384) return launch_gemv<MODE, 2, 2, 4, STAGE>(p, st);
+    if (p.K >= 8192) return launch_gemv<MODE, 2, 4, 2, STAGE>(p, st);     // swept (benchmarks/gemv_tune.py): 24.2 us vs 27.0 for <4,8,2>
+    if (p.N < 16384) return launch_gemv<MODE, 4, 4, 4, STAGE>(p, st);     // 6.9 us vs 7.9 for <2,2,4> (o_proj 3584 x 3584)
     return launch_gemv<MODE, 4, 1, 2, STAGE>(p, st);
 }
 
