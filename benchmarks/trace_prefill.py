@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from streaming_vlm_b200 import _abi
-_abi.LIB_PATH = os.path.join(ROOT, "benchmarks", "_trace", "libsvlm_trace.so")
+_abi.LIB_PATH = os.path.join(ROOT, "benchmarks", "_trace", os.environ.get("SVLM_TRACE_LIB", "libsvlm_trace.so"))
 from streaming_vlm_b200.config import QWEN25VL_7B as G
 from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
 
@@ -16,19 +16,20 @@ c = StreamingCache(G, n + 512, dev)
 c.arena[0].normal_(0, 0.5)
 HQ, D = G.num_heads, G.head_dim
 mt = -(-tq // 18)
-trace = torch.zeros(splits * 4 * mt * 32 * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(splits * 4 * mt * 32 * 16 + 4096, dtype=torch.int64, device=dev)
 os.environ["SVLM_TRACE_PTR"] = str(trace.data_ptr())
 q = torch.randn(tq, HQ, D, device=dev).to(torch.bfloat16); o = torch.empty_like(q)
 ws = torch.zeros(_abi.attn_workspace_bytes(tq, HQ, D, splits) // 4 + 16, dtype=torch.float32, device=dev)
 for it in range(3):
     _abi.attn_causal(c.view, 0, it, q, o, tq, HQ, n, 1 / math.sqrt(D), splits, ws)
 torch.cuda.synchronize()
-t = trace.view(splits, 4, mt, 32, 16).cpu()
-tt = t[0, 1, 3]
-nt = int((tt[:, 1] > 0).sum())
-base = int(tt[0, 0])
-ev = ["top", "s_seen", "ld", "bar_issue", "arrived"]
-for j in range(6, min(nt, 8)):
-    for name, o in (("w2 smsp2 half0", 0), ("w6 smsp2 half1", 5), ("w4 smsp0 half0", 10)):
-        print(j, name, " ".join(f"{ev[e]}={int(tt[j, o + e]) - base:6d}" for e in range(5)))
-print("cycles/tile:", (int(tt[nt - 1, 4]) - int(tt[1, 4])) / (nt - 2))
+t = trace.view(-1, 32, 16).cpu()
+cnt = (t[:, :, 1] > 0).sum(1)
+cta = int(cnt.argmax())
+tt = t[cta]
+nt = int(cnt[cta])
+base = int(tt[6, 0])
+print("cta", cta, "tiles", nt)
+for j in range(6, min(nt, 9)):
+    print(j, " ".join(f"w{w + 2}:{int(tt[j, 2 * w]) - base}->{int(tt[j, 2 * w + 1]) - base}({int(tt[j, 2 * w + 1]) - int(tt[j, 2 * w])})" for w in range(8)))
+print("cycles/tile:", (int(tt[nt - 1, 1]) - int(tt[2, 1])) / (nt - 3))

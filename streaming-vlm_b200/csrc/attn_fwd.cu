@@ -52,7 +52,7 @@ struct AttnParams {
 };
 
 #ifdef SVLM_TRACE
-#define ATRACE(ev, tile) do { if (p.trace && (tile) < 32) p.trace[((((blockIdx.z * gridDim.y) + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (tile)) * 8 + (ev)] = clock64(); } while (0)
+#define ATRACE(ev, tile) do { if (p.trace && (tile) < 32) p.trace[((((blockIdx.z * gridDim.y) + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (tile)) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define ATRACE(ev, tile) do { } while (0)
 #endif
@@ -150,7 +150,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint32_t ph = (j / ATT_STAGES) & 1;
                 const int row = (my_begin + j) * BN;
                 mbar_wait(&bars->k_empty[s], ph ^ 1);
-                if (lane == 0) ATRACE(7, j);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars->k_full[s], TILE_BYTES);
                     tma_load_3d(sK + s * TILE_BYTES, &tmK, &bars->k_full[s], 0, row, kv_coord);
@@ -210,9 +209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     __syncwarp();
                 }
                 const int s = j % ATT_STAGES;
-                if (lane == 0) ATRACE(5, j);
                 mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);
-                if (lane == 0) ATRACE(6, j);
                 mbar_wait(&bars->v_full[s], (j / ATT_STAGES) & 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -236,7 +233,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int tok = tok0 + row / p.G;
         const int g = row % p.G;
         const bool valid = (row < p.G * p.tpt) && (tok < p.Tq);
-        int lo = 0, hi = 0;
+        // Rows of the tile that carry no query (row >= G * tpt, or token >= Tq) are never masked: their output is discarded, and a
+        // permanently "masked" lane would drag its whole warp through the slow masked path on every tile.
+        int lo = 0, hi = 0x7fffffff;
         if (valid) {
             if (MODE == MODE_CAUSAL) {
                 hi = min(kv_len, off + tok + 1);
@@ -250,16 +249,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
             const int kv0 = (my_begin + j) * BN + half * 64;
-            if (threadIdx.x == 64) ATRACE(0, j);
             mbar_wait(&bars->s_full[b], (j >> 1) & 1);
             tc_fence_after();
-            if (threadIdx.x == 64) ATRACE(1, j);
             uint32_t sr[2][32];
 #pragma unroll
             for (int c = 0; c < 2; ++c) tmem_ld32(tmem + lane_addr + b * 128 + half * 64 + c * 32, sr[c]);
             tmem_wait_ld();
-            if (threadIdx.x == 64) ATRACE(2, j);
-            const bool need_mask = (kv0 < lo) || (kv0 + 64 > hi);
+            // warp-uniform, so the warp is converged at the named barrier below
+            const bool need_mask = __any_sync(0xffffffffu, (kv0 < lo) || (kv0 + 64 > hi));
             float mt_raw = -INFINITY;                      // max of the RAW scores (scale > 0 keeps the order)
             if (need_mask) {
 #pragma unroll
@@ -280,7 +277,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             bars->xmax[b][half][row] = mt_raw;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) ATRACE(3, j);
+            if (lane == 0) ATRACE((warp - 2) * 2, j);
             const float mt = fmaxf(mt_raw, bars->xmax[b][half ^ 1][row]) * p.scale_log2;
             const bool upd = mt > m_run + RESCALE_THRESHOLD;      // also true for the first finite tile (m_run = -inf)
             const float m_new = upd ? mt : m_run;
@@ -322,10 +319,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float lsum0 = lo2(lsum2), lsum1 = hi2(lsum2);
             l_run = l_run * alpha + (lsum0 + lsum1);
             m_run = m_new;
+            if (lane == 0) ATRACE((warp - 2) * 2 + 1, j);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bars->p_full[b]);
-            if (threadIdx.x == 64) ATRACE(4, j);
         }
 
         // ---- epilogue: the two halves add their row sums, each stores its 64 output columns ----
