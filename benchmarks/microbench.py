@@ -112,7 +112,7 @@ def main():
         o1 = torch.empty_like(q1)
         kv_dev = torch.tensor([keep], dtype=torch.int32, device=dev)
         best = None
-        for splits in sorted({8, 16, 37, 74, min(148, (keep + 127) // 128)}):
+        for splits in sorted({8, 16, 37, 74, 111, min(148, (keep + 127) // 128)}):
             ws = torch.zeros(_abi.attn_workspace_bytes(1, HQ, D, splits) // 4 + 16, dtype=torch.float32, device=dev)
 
             def dec():

@@ -196,6 +196,11 @@ int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, f
                         int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
                         int32_t* next_pos, void* stream);
 
+/* Scheduling aid of the decode loop (no reference counterpart: the reference leaves cache policy to the libraries it
+ * calls): issues L2 prefetches for [ptr, ptr + bytes).  The session runner launches it on a side stream next to the
+ * latency-bound decode attention so that the weights of the following projections are L2-resident when they start. */
+int svlm_prefetch_l2(const void* ptr, size_t bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (the reference-facing plugin call with HOST data):
  * copy in, run, copy out, synchronise.  Used by bench.py's end-to-end leg and by callers that

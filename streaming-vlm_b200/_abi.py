@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_kv_compact_rope_host"]
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
 
@@ -86,6 +86,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemv_bf16.argtypes = [vp, vp, vp, c_float, vp, vp, vp, c_int, c_int, c_int, vp]
     L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -220,6 +221,14 @@ def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, 
     check(lib().svlm_lm_head_argmax(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
                                     key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
                                     next_pos.data_ptr(), _stream()), "svlm_lm_head_argmax")
+
+
+def prefetch_l2(t, nbytes=None):
+    """Issue L2 prefetches for the first `nbytes` (default: all) of the contiguous tensor `t` on the current stream."""
+    _req_cuda(t)
+    total = t.numel() * t.element_size()
+    n = total if nbytes is None else min(int(nbytes), total)
+    check(lib().svlm_prefetch_l2(t.data_ptr(), n, _stream()), "svlm_prefetch_l2")
 
 
 def add_rmsnorm(a, b, weight, out_sum, out_norm, eps: float):

@@ -19,12 +19,16 @@
 namespace svlm {
 
 constexpr int DEC_BN = 128;
-constexpr int DEC_STAGES = 3;
+// K and V tiles alternate through ONE ring of 32 KB slots (use u = 2j for K(j), 2j + 1 for V(j); slot = u % SLOTS), which
+// keeps a CTA at ~107 KB of shared memory: two CTAs per SM interleave their (latency-bound) per-tile chains.
+// SLOTS = 3 when the grid has more CTAs than SMs (two resident CTAs hide each other's stalls), 6 (one CTA per SM, two tiles of
+// look-ahead) otherwise.
+constexpr int DEC_MAX_SLOTS = 6;
 constexpr int DEC_PANEL = 128 * 128;           // 128 keys x 64 dims
 constexpr int DEC_TILE = 2 * DEC_PANEL;        // 128 keys x 128 dims
 constexpr int DEC_QP_PANEL = 16 * 128;         // 16 rows x 64 elements (Q and P^T operands)
 constexpr int DEC_THREADS = 192;
-constexpr int DEC_SMEM = 1024 + 2 * DEC_STAGES * DEC_TILE + 2 * DEC_QP_PANEL + 2 * 2 * DEC_QP_PANEL + 1024;
+constexpr int dec_smem(int slots) { return 1024 + slots * DEC_TILE + 2 * DEC_QP_PANEL + 2 * 2 * DEC_QP_PANEL + 1024; }
 
 struct DecParams {
     int Hq, G, D;
@@ -47,8 +51,7 @@ struct DecParams {
 
 struct DecShared {
     uint64_t q_full;
-    uint64_t k_full[DEC_STAGES], k_empty[DEC_STAGES];
-    uint64_t v_full[DEC_STAGES], v_empty[DEC_STAGES];
+    uint64_t full[DEC_MAX_SLOTS], empty[DEC_MAX_SLOTS];
     uint64_t s_full[2], p_full[2];
     uint64_t o_done[2];
     uint32_t tmem_base;
@@ -76,15 +79,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  : "memory");
 }
 
-template <int G>
-__global__ void __launch_bounds__(DEC_THREADS, 1)
+template <int G, int DEC_SLOTS>
+__global__ void __launch_bounds__(DEC_THREADS, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const DecParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sK = smem;
-    uint8_t* sV = sK + DEC_STAGES * DEC_TILE;
-    uint8_t* sQ = sV + DEC_STAGES * DEC_TILE;            // 2 panels of [16 heads][64 dims]
+    uint8_t* sKV = smem;                                  // ring of K / V tiles
+    uint8_t* sQ = sKV + DEC_SLOTS * DEC_TILE;            // 2 panels of [16 heads][64 dims]
     uint8_t* sP = sQ + 2 * DEC_QP_PANEL;                 // 2 buffers x 2 panels of [16 heads][64 keys]
     DecShared* sh = reinterpret_cast<DecShared*>(sP + 2 * 2 * DEC_QP_PANEL);
 
@@ -94,10 +96,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(&sh->q_full, 1);
-        for (int s = 0; s < DEC_STAGES; ++s) {
-            mbar_init(&sh->k_full[s], 1); mbar_init(&sh->k_empty[s], 1);
-            mbar_init(&sh->v_full[s], 1); mbar_init(&sh->v_empty[s], 1);
-        }
+        for (int s = 0; s < DEC_SLOTS; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&sh->s_full[b], 1); mbar_init(&sh->p_full[b], 128); mbar_init(&sh->o_done[b], 1); }
         fence_barrier_init();
     }
@@ -109,6 +108,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh->tmem_base;
+    // everything above (barriers, TMEM, zeroed P^T) overlapped the tail of the QKV kernel; q, the new arena row and the
+    // device-side length are its outputs
+    pdl_trigger();
+    pdl_wait();
 
     const int kv_len = p.kv_len_dev ? __ldg(p.kv_len_dev) : p.kv_len;
     const int n_total = (kv_len + DEC_BN - 1) / DEC_BN;
@@ -129,23 +132,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, 0);
             }
             __syncwarp();
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % DEC_STAGES;
-                const uint32_t ph = (j / DEC_STAGES) & 1;
-                const int row = (my_begin + j) * DEC_BN;
-                mbar_wait(&sh->k_empty[s], ph ^ 1);
-                TRACE(7, j);
+            for (int u = 0; u < 2 * n_tiles; ++u) {
+                const int s = u % DEC_SLOTS;
+                const int row = (my_begin + (u >> 1)) * DEC_BN;
+                mbar_wait(&sh->empty[s], ((u / DEC_SLOTS) & 1) ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&sh->k_full[s], DEC_TILE);
-                    tma_load_3d(sK + s * DEC_TILE, &tmK, &sh->k_full[s], 0, row, kv_coord);
-                    tma_load_3d(sK + s * DEC_TILE + DEC_PANEL, &tmK, &sh->k_full[s], 64, row, kv_coord);
-                }
-                __syncwarp();
-                mbar_wait(&sh->v_empty[s], ph ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&sh->v_full[s], DEC_TILE);
-                    tma_load_3d(sV + s * DEC_TILE, &tmV, &sh->v_full[s], 0, row, kv_coord);
-                    tma_load_3d(sV + s * DEC_TILE + DEC_PANEL, &tmV, &sh->v_full[s], 64, row, kv_coord);
+                    const CUtensorMap* tm = (u & 1) ? &tmV : &tmK;
+                    mbar_arrive_expect_tx(&sh->full[s], DEC_TILE);
+                    tma_load_3d(sKV + s * DEC_TILE, tm, &sh->full[s], 0, row, kv_coord);
+                    tma_load_3d(sKV + s * DEC_TILE + DEC_PANEL, tm, &sh->full[s], 64, row, kv_coord);
                 }
                 __syncwarp();
             }
@@ -157,7 +152,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (n_tiles > 0) {
             const uint32_t q_addr = smem_u32(sQ);
             auto issue_s = [&](int stage, int buf) {
-                const uint32_t k_addr = smem_u32(sK + stage * DEC_TILE);
+                const uint32_t k_addr = smem_u32(sKV + stage * DEC_TILE);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint32_t ka = k_addr + (uint32_t)(kk >> 2) * DEC_PANEL + (uint32_t)(kk & 3) * 32u;
@@ -166,7 +161,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             };
             auto issue_o = [&](int stage, int buf, bool acc) {
-                const uint32_t v_addr = smem_u32(sV + stage * DEC_TILE);
+                const uint32_t v_addr = smem_u32(sKV + stage * DEC_TILE);
                 const uint32_t p_addr = smem_u32(sP + buf * 2 * DEC_QP_PANEL);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
@@ -177,33 +172,33 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             };
             mbar_wait(&sh->q_full, 0);
-            mbar_wait(&sh->k_full[0], 0);
+            mbar_wait(&sh->full[0], 0);
             tc_fence_after();
             if (elect_one()) {
                 issue_s(0, 0);
-                umma_commit(&sh->k_empty[0]);
+                umma_commit(&sh->empty[0]);
                 umma_commit(&sh->s_full[0]);
             }
             __syncwarp();
             for (int j = 0; j < n_tiles; ++j) {
                 if (j + 1 < n_tiles) {
-                    const int s1 = (j + 1) % DEC_STAGES;
-                    mbar_wait(&sh->k_full[s1], ((j + 1) / DEC_STAGES) & 1);
+                    const int u1 = 2 * (j + 1), s1 = u1 % DEC_SLOTS;
+                    mbar_wait(&sh->full[s1], (u1 / DEC_SLOTS) & 1);
                     tc_fence_after();
                     if (elect_one()) {
                         issue_s(s1, (j + 1) & 1);
-                        umma_commit(&sh->k_empty[s1]);
+                        umma_commit(&sh->empty[s1]);
                         umma_commit(&sh->s_full[(j + 1) & 1]);
                     }
                     __syncwarp();
                 }
-                const int s = j % DEC_STAGES;
+                const int u = 2 * j + 1, s = u % DEC_SLOTS;
                 mbar_wait(&sh->p_full[j & 1], (j >> 1) & 1);
-                mbar_wait(&sh->v_full[s], (j / DEC_STAGES) & 1);
+                mbar_wait(&sh->full[s], (u / DEC_SLOTS) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_o(s, j & 1, j > 0);
-                    umma_commit(&sh->v_empty[s]);
+                    umma_commit(&sh->empty[s]);
                     umma_commit(&sh->o_done[j & 1]);
                 }
                 __syncwarp();
@@ -319,6 +314,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int h = 0; h < G; ++h)
                 if (row == h) p.part_ml[(int64_t)split * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
+
         }
     }
 
@@ -327,19 +323,24 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 1) tmem_dealloc<64>(tmem);
 }
 
-template <int G>
-static int launch_decode(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
+template <int G, int SLOTS>
+static int launch_decode_s(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<G, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem(SLOTS));
         if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", DEC_SMEM, cudaGetErrorString(e));
+            set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", dec_smem(SLOTS), cudaGetErrorString(e));
             return SVLM_ECUDA;
         }
         attr_done = true;
     }
-    attn_decode_kernel<G><<<grid, DEC_THREADS, DEC_SMEM, st>>>(tq, tk, tv, p);
+    launch_pdl(attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, tq, tk, tv, p);
     return launch_status("attn_decode_kernel");
+}
+
+template <int G>
+static int launch_decode(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
+    return grid.x * grid.y * grid.z > 148 ? launch_decode_s<G, 3>(tq, tk, tv, p, grid, st) : launch_decode_s<G, 6>(tq, tk, tv, p, grid, st);
 }
 
 static int launch_decode_g(int G, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid,
@@ -398,7 +399,9 @@ int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const v
 #endif
     if ((rc = launch_decode_g(G, tq, tk, tv, p, dim3(num_splits, H), st))) return rc;
     if (num_splits > 1) {
-        attn_combine_kernel<<<q_heads, 128, 0, st>>>(p.part_o, p.part_ml, p.out, q_heads, D, num_splits);
+        // A separate merge launch beats an in-kernel "last CTA merges" epilogue here (measured: 10.2 vs 12.6 us per layer at
+        // 4k keys, 30.1 vs 33.7 us at 64k): 28 one-head CTAs finish the merge in one load latency.
+        launch_pdl(attn_combine_kernel, dim3(q_heads), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out, q_heads, D, num_splits);
         return launch_status("attn_combine_kernel");
     }
     return SVLM_OK;

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -41,6 +42,40 @@ inline int launch_status(const char* what) {
     }
     return SVLM_OK;
 }
+
+// ------------------------------------------------------------------------------------ programmatic dependent launch
+// The decode step is a chain of ~170 short kernels per token.  Kernels launched through launch_pdl() may start while
+// their predecessor in the stream is still draining: everything before pdl_wait() (barrier/TMEM setup, prefetch of
+// immutable weights) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and
+// its writes are visible, so all reads of mutable data and all writes come after it.  OFF by default (the device-side
+// instructions are then no-ops): measured on B200 it LOSES 7 ms per chunk (70.8 vs 63.9 ms) -- successor CTAs parked at
+// the wait take SM slots from the weight-streaming GEMVs.  SVLM_PDL=1 enables the attribute for experiments.
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SVLM_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors are picked up by launch_status()
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // Arena addressing (elements).  Layout: [2][3][L][H][cap][D].
 struct ArenaDims {

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
     __shared__ unsigned long long best[GROUPS * RG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = p.K;
+    pdl_trigger();      // programmatic dependent launch: the successor's CTAs may become resident while this grid runs
+    pdl_wait();         // x / residual are the predecessor's outputs
 
     // ---- prologue: stage x (RMS-normalised when norm_w is given) in shared memory; plain/residual GEMVs without a
     // norm read x straight from global memory (L1-resident after the first warp) and need no block barrier here
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
 
 // token id + device-side counters of the decode loop (kv length before / after the next step, next text position)
 __global__ void decode_finalize_kernel(unsigned long long* key, int64_t* tok, int32_t* kv_len, int32_t* kv_after, int32_t* next_pos) {
+    pdl_wait();
     const unsigned long long k = *key;
     *tok = (int64_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
     *key = 0ull;
@@ -252,6 +255,15 @@ __global__ void decode_finalize_kernel(unsigned long long* key, int64_t* tok, in
     *kv_len = n;
     *kv_after = n + 1;
     *next_pos = *next_pos + 1;
+}
+
+// Pull a byte range into L2 (one prefetch per 128-byte line, no register or shared-memory footprint).  Launched on a side
+// stream next to the latency-bound decode attention: HBM is idle there, so the o_proj weights and the head of the gate/up
+// weights stream in while attention runs and the following GEMVs start from L2.
+__global__ void __launch_bounds__(256) prefetch_l2_kernel(const uint8_t* __restrict__ base, size_t bytes) {
+    const size_t lines = (bytes + 127) >> 7;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (i << 7)));
 }
 
 template <int MODE, int RG, int KS, int U, bool STAGE>
@@ -268,7 +280,7 @@ static int launch_gemv(const GemvParams& p, cudaStream_t st) {
     }
     const int rows_per_cta = (8 / KS) * RG;
     const int grid = (p.N + rows_per_cta - 1) / rows_per_cta;      // QKV: RG = 2 -> one group per (n, n+64) pair, same count
-    gemv_kernel<MODE, RG, KS, U, STAGE><<<grid, GEMV_THREADS, smem, st>>>(p);
+    launch_pdl(gemv_kernel<MODE, RG, KS, U, STAGE>, dim3(grid), dim3(GEMV_THREADS), smem, st, p);
     return launch_status("gemv_kernel");
 }
 
@@ -361,7 +373,7 @@ extern "C" int svlm_lm_head_argmax(const void* W, const void* x, const void* nor
     GemvParams p{(const uint16_t*)W, (const uint16_t*)x, (const uint16_t*)norm_weight, eps, nullptr, nullptr, nullptr, N, K, suppress,
                  (unsigned long long*)key_scratch};
     if ((rc = dispatch_rw<GEMV_ARGMAX>(p, (cudaStream_t)stream))) return rc;
-    decode_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
+    launch_pdl(decode_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
     return launch_status("decode_finalize_kernel");
 }
 
@@ -391,4 +403,15 @@ extern "C" int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, 
     p.row_dev = row_dev; p.pos_dev = pos_dev;
     p.cos_tab = (const uint16_t*)cos_table; p.sin_tab = (const uint16_t*)sin_table; p.tab_rows = table_rows;
     return launch_gemv<GEMV_QKV, 2, 2, 4, true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int svlm_prefetch_l2(const void* ptr, size_t bytes, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(ptr != nullptr, "NULL pointer");
+    if (bytes == 0) return SVLM_OK;
+    const size_t lines = (bytes + 127) >> 7;
+    const unsigned grid = (unsigned)((lines + 256 * 16 - 1) / (256 * 16) < 296 ? (lines + 256 * 16 - 1) / (256 * 16) : 296);
+    prefetch_l2_kernel<<<grid ? grid : 1, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)ptr, bytes);
+    return launch_status("prefetch_l2_kernel");
 }

@@ -21,6 +21,7 @@ kernel of `libsvlm_b200.so`.  Section timers mirror the reference's PKV / GEN (`
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
@@ -103,7 +104,7 @@ class StreamingEngine:
         self.suppress = None if suppress is None else suppress.to(self.device)
         self.cache = StreamingCache(geo, capacity, self.device)
         self.scale = 1.0 / math.sqrt(geo.head_dim)
-        self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 148 // geo.num_kv_heads))
+        self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 296 // geo.num_kv_heads))   # two CTAs per SM
         self.prefill_splits = prefill_splits
         self._prepare_weights(weights)
         g = geo
@@ -117,6 +118,11 @@ class StreamingEngine:
         self._graphs = {}
         self._dec_qkv = torch.zeros((g.num_heads + 2 * g.num_kv_heads) * g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_q = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+        # side stream of the decode step: L2 prefetch of the o_proj weights and the head of the gate/up weights while the
+        # (latency-bound, HBM-idle) attention runs; SVLM_DECODE_PREFETCH_MB = MiB of gate/up to pull (0 disables the branch)
+        self._side = torch.cuda.Stream(device=dev)
+        self._prefetch_gu_bytes = int(float(os.environ.get("SVLM_DECODE_PREFETCH_MB", "32")) * (1 << 20))
+        self._prefetch = os.environ.get("SVLM_DECODE_PREFETCH", "1") != "0"
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
         self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -373,12 +379,21 @@ class StreamingEngine:
         for li, L in enumerate(self.layers):
             _abi.gemv_qkv_rope_append(c.view, c.cur, li, L["wqkv"], x, L["ln1"], g.rms_eps, L["bqkv"], hq, q_rot, self.kv_len_dev,
                                       c.next_pos, c.cos_table, c.sin_table)
+            if self._prefetch:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    _abi.prefetch_l2(L["wo"])
+                    if self._prefetch_gu_bytes:
+                        _abi.prefetch_l2(L["wgu"], self._prefetch_gu_bytes)
             _abi.attn_causal(c.view, c.cur, li, q_rot, o, 1, hq, c.capacity, self.scale, self._splits_now,
                              self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev)
+            if self._prefetch:
+                main.wait_stream(self._side)
             _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
             _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
             _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
-        self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0))
+        self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0) + ((2 if self._prefetch_gu_bytes else 1) if self._prefetch else 0))
         _abi.lm_head_argmax(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
                             self.kv_len_dev, self.kv_after_dev, c.next_pos)
         self.launches += 2

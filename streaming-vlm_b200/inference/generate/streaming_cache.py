@@ -91,7 +91,7 @@ class StreamingCache:
         self.value_cache = _PlaneList(self, V_PLANE)
         self._rot_stale = False
         self.compactions = 0
-        self.decode_splits = max(1, min((self.capacity + 127) // 128, 148 // self.kv_heads))
+        self.decode_splits = max(1, min((self.capacity + 127) // 128, 296 // self.kv_heads))
         self._pending_start = 0
 
     # ------------------------------------------------------------------ reference interface
