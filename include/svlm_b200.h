@@ -40,6 +40,7 @@ extern "C" {
 #define SVLM_ENODEV   -3   /* no sm_100 device / driver entry point unavailable */
 
 #define SVLM_MAX_RUNS 32   /* maximum number of gather runs per compaction launch */
+#define SVLM_MAX_STREAMS 8 /* streams whose decode steps share one launch (section 8) */
 
 #define SVLM_PLANE_K_RAW 0
 #define SVLM_PLANE_K_ROT 1
@@ -195,6 +196,32 @@ int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, 
 int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
                         int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
                         int32_t* next_pos, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (8) Decode step of SEVERAL independent streams in one launch (the reference runs one stream per process,
+ * eval/livesports3kcc/distributed_generate_streaming.py:53-62; streams that share a GPU share one sweep of the
+ * weights here, and their split-KV attention becomes one grid that is large enough to be HBM-bound).
+ * Every stream has its own arena of the SAME geometry (`geometry->base` is ignored) and its own device-side
+ * counters; `slots` is a HOST array of n_streams <= SVLM_MAX_STREAMS entries, read at launch time.
+ *   svlm_qkv_rope_append_streams : token b of q/k/v [n_streams][...] is rotated at text position *pos_dev (all three
+ *       mRoPE axes) and appended to row *row_dev of stream b (same arithmetic as svlm_qkv_rope_append).
+ *   svlm_attn_decode_streams     : q, out bf16 [n_streams][Hq][D]; stream b attends to its first *kv_len_dev rows.
+ *       workspace: svlm_attn_workspace_bytes(n_streams, Hq, D, num_splits) bytes when num_splits > 1.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    void*          arena_base;   /* this stream's arena (buffer 0, plane 0) */
+    int32_t        buffer;       /* its live ping-pong buffer */
+    const int32_t* row_dev;      /* device scalar: arena row of the token being appended */
+    const int32_t* pos_dev;      /* device scalar: its text position */
+    const int32_t* kv_len_dev;   /* device scalar: rows to attend to (including the appended token) */
+} svlm_stream_slot_t;
+int svlm_qkv_rope_append_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
+                                 const void* q, const void* k, const void* v, int64_t q_row_stride, int64_t k_row_stride,
+                                 int64_t v_row_stride, int q_heads, void* q_out, const void* cos_table, const void* sin_table,
+                                 int table_rows, const int32_t* mrope_section_host, void* stream);
+int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
+                             const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
+                             size_t workspace_bytes, float scale, void* stream);
 
 /* Scheduling aid of the decode loop (no reference counterpart: the reference leaves cache policy to the libraries it
  * calls): issues L2 prefetches for [ptr, ptr + bytes).  The session runner launches it on a side stream next to the

@@ -23,7 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_kv_compact_rope_host"]
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
+           "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
 
@@ -31,6 +32,14 @@ MAX_RUNS = 32
 class Arena(Structure):
     _fields_ = [("base", c_void_p), ("layers", c_int32), ("kv_heads", c_int32), ("head_dim", c_int32),
                 ("capacity", c_int32)]
+
+
+class StreamSlot(Structure):
+    """`svlm_stream_slot_t` (include/svlm_b200.h section 8)."""
+    _fields_ = [("arena_base", c_void_p), ("buffer", c_int32), ("row_dev", c_void_p), ("pos_dev", c_void_p), ("kv_len_dev", c_void_p)]
+
+
+MAX_STREAMS = 8
 
 
 def needs_build() -> bool:
@@ -87,6 +96,10 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
+    L.svlm_qkv_rope_append_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int,
+                                               vp, vp, vp, c_int, i32p, vp]
+    L.svlm_attn_decode_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_size_t,
+                                           c_float, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -221,6 +234,38 @@ def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, 
     check(lib().svlm_lm_head_argmax(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
                                     key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
                                     next_pos.data_ptr(), _stream()), "svlm_lm_head_argmax")
+
+
+def make_slots(caches, row_devs, pos_devs, kv_len_devs):
+    """HOST array of `svlm_stream_slot_t`, one per stream: arena + live buffer of `caches[b]`, and the device scalars that name
+    the row / position of the token being appended and the attention bound."""
+    n = len(caches)
+    if not 1 <= n <= MAX_STREAMS:
+        raise ValueError(f"1..{MAX_STREAMS} streams per launch, got {n}")
+    arr = (StreamSlot * n)()
+    for b, c in enumerate(caches):
+        arr[b].arena_base = c.arena.data_ptr()
+        arr[b].buffer = c.cur
+        arr[b].row_dev = row_devs[b].data_ptr()
+        arr[b].pos_dev = pos_devs[b].data_ptr()
+        arr[b].kv_len_dev = kv_len_devs[b].data_ptr()
+    return arr
+
+
+def qkv_rope_append_streams(geometry: "ArenaView", slots, layer, q, k, v, q_heads, q_out, cos_table, sin_table, section):
+    """Decode step of len(slots) streams: row b of q/k/v goes to stream b (see include/svlm_b200.h section 8)."""
+    _req_cuda(q, k, v, q_out)
+    check(lib().svlm_qkv_rope_append_streams(geometry.ref, slots, len(slots), layer, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0),
+                                             k.stride(0), v.stride(0), q_heads, q_out.data_ptr(), cos_table.data_ptr(),
+                                             sin_table.data_ptr(), cos_table.shape[0], i32_array(section), _stream()), "svlm_qkv_rope_append_streams")
+
+
+def attn_decode_streams(geometry: "ArenaView", slots, layer, q, out, q_heads, max_kv_len, scale, num_splits, workspace):
+    _req_cuda(q, out)
+    ws_ptr = workspace.data_ptr() if workspace is not None else None
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    check(lib().svlm_attn_decode_streams(geometry.ref, slots, len(slots), layer, q.data_ptr(), out.data_ptr(), q_heads, max_kv_len,
+                                         num_splits, ws_ptr, ws_bytes, scale, _stream()), "svlm_attn_decode_streams")
 
 
 def prefetch_l2(t, nbytes=None):

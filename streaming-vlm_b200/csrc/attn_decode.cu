@@ -32,13 +32,14 @@ constexpr int dec_smem(int slots) { return 1024 + slots * DEC_TILE + 2 * DEC_QP_
 
 struct DecParams {
     int Hq, G, D;
-    int kv_len;
-    const int32_t* kv_len_dev;
+    int kv_len;                                       // host value, used for streams whose kv_len_dev is NULL
+    const int32_t* kv_len_dev[SVLM_MAX_STREAMS];      // per stream (blockIdx.z)
+    int rows_total;                                   // n_streams * Hq: row count of out / the partials
     int num_splits;
     int kv_head_base;
-    uint16_t* out;        // bf16 [Hq][D]           (num_splits == 1)
-    float* part_o;        // fp32 [splits][Hq][D]
-    float2* part_ml;      // (m, l) [splits][Hq]
+    uint16_t* out;        // bf16 [streams][Hq][D]           (num_splits == 1)
+    float* part_o;        // fp32 [splits][streams * Hq][D]
+    float2* part_ml;      // (m, l) [splits][streams * Hq]
     float scale_log2;
     unsigned long long* trace;   // SVLM_TRACE builds only: [cta][tile][8] clock64 stamps
 };
@@ -79,10 +80,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  : "memory");
 }
 
+// One K and one V tensor map per stream (every stream owns its arena); q is one [streams][Hq][D] tensor.
+struct DecMaps {
+    CUtensorMap q;
+    CUtensorMap k[SVLM_MAX_STREAMS];
+    CUtensorMap v[SVLM_MAX_STREAMS];
+};
+
 template <int G, int DEC_SLOTS>
 __global__ void __launch_bounds__(DEC_THREADS, 2)
-attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const DecParams p) {
+attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
+    const int strm = blockIdx.z;
+    const CUtensorMap& tmQ = maps.q;
+    const CUtensorMap& tmK = maps.k[strm];
+    const CUtensorMap& tmV = maps.v[strm];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sKV = smem;                                  // ring of K / V tiles
@@ -113,7 +124,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     pdl_trigger();
     pdl_wait();
 
-    const int kv_len = p.kv_len_dev ? __ldg(p.kv_len_dev) : p.kv_len;
+    const int kv_len = p.kv_len_dev[strm] ? __ldg(p.kv_len_dev[strm]) : p.kv_len;
     const int n_total = (kv_len + DEC_BN - 1) / DEC_BN;
     const int tps = (n_total + p.num_splits - 1) / p.num_splits;
     const int my_begin = split * tps;
@@ -128,8 +139,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (n_tiles > 0) {
             if (elect_one()) {
                 mbar_arrive_expect_tx(&sh->q_full, 2 * DEC_QP_PANEL);
-                tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, 0);
-                tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, 0);
+                tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, strm);
+                tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, strm);
             }
             __syncwarp();
             for (int u = 0; u < 2 * n_tiles; ++u) {
@@ -301,19 +312,19 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (d < p.D) {
 #pragma unroll
             for (int h = 0; h < G; ++h) {
-                const int hq = head * G + h;
+                const int hq = strm * p.Hq + head * G + h;       // row of out / the partials
                 if (p.num_splits == 1) {
                     const float inv = l_tot[h] > 0.f ? 1.0f / l_tot[h] : 0.f;
                     p.out[(int64_t)hq * p.D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(orow[h]) * inv));
                 } else {
-                    p.part_o[((int64_t)split * p.Hq + hq) * p.D + d] = __uint_as_float(orow[h]);
+                    p.part_o[((int64_t)split * p.rows_total + hq) * p.D + d] = __uint_as_float(orow[h]);
                 }
             }
         }
         if (p.num_splits > 1) {
 #pragma unroll
             for (int h = 0; h < G; ++h)
-                if (row == h) p.part_ml[(int64_t)split * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
+                if (row == h) p.part_ml[(int64_t)split * p.rows_total + strm * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
 
         }
     }
@@ -324,7 +335,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 template <int G, int SLOTS>
-static int launch_decode_s(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
+static int launch_decode_s(const DecMaps& maps, const DecParams& p, dim3 grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<G, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem(SLOTS));
@@ -334,26 +345,25 @@ static int launch_decode_s(const CUtensorMap& tq, const CUtensorMap& tk, const C
         }
         attr_done = true;
     }
-    launch_pdl(attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, tq, tk, tv, p);
+    launch_pdl(attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, maps, p);
     return launch_status("attn_decode_kernel");
 }
 
 template <int G>
-static int launch_decode(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid, cudaStream_t st) {
-    return grid.x * grid.y * grid.z > 148 ? launch_decode_s<G, 3>(tq, tk, tv, p, grid, st) : launch_decode_s<G, 6>(tq, tk, tv, p, grid, st);
+static int launch_decode(const DecMaps& maps, const DecParams& p, dim3 grid, cudaStream_t st) {
+    return grid.x * grid.y * grid.z > 148 ? launch_decode_s<G, 3>(maps, p, grid, st) : launch_decode_s<G, 6>(maps, p, grid, st);
 }
 
-static int launch_decode_g(int G, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const DecParams& p, dim3 grid,
-                           cudaStream_t st) {
+static int launch_decode_g(int G, const DecMaps& maps, const DecParams& p, dim3 grid, cudaStream_t st) {
     switch (G) {
-        case 1: return launch_decode<1>(tq, tk, tv, p, grid, st);
-        case 2: return launch_decode<2>(tq, tk, tv, p, grid, st);
-        case 3: return launch_decode<3>(tq, tk, tv, p, grid, st);
-        case 4: return launch_decode<4>(tq, tk, tv, p, grid, st);
-        case 5: return launch_decode<5>(tq, tk, tv, p, grid, st);
-        case 6: return launch_decode<6>(tq, tk, tv, p, grid, st);
-        case 7: return launch_decode<7>(tq, tk, tv, p, grid, st);
-        case 8: return launch_decode<8>(tq, tk, tv, p, grid, st);
+        case 1: return launch_decode<1>(maps, p, grid, st);
+        case 2: return launch_decode<2>(maps, p, grid, st);
+        case 3: return launch_decode<3>(maps, p, grid, st);
+        case 4: return launch_decode<4>(maps, p, grid, st);
+        case 5: return launch_decode<5>(maps, p, grid, st);
+        case 6: return launch_decode<6>(maps, p, grid, st);
+        case 7: return launch_decode<7>(maps, p, grid, st);
+        case 8: return launch_decode<8>(maps, p, grid, st);
         default: set_error("decode attention supports 1..8 query heads per kv head (got %d)", G); return SVLM_EINVAL;
     }
 }
@@ -366,45 +376,88 @@ static void* getenv_ptr(const char* name) {
 }
 #endif
 
-int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
-                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st) {
-    const int D = arena->head_dim, H = arena->kv_heads, G = q_heads / H;
-    ArenaDims ad{arena->layers, H, D, arena->capacity};
-    const uint16_t* base = (const uint16_t*)arena->base;
-    CUtensorMap tq, tk, tv;
+// Shared by the single-stream entry (svlm_attn_causal with Tq = 1) and svlm_attn_decode_streams.
+static int decode_launch_common(const svlm_arena_t* geom, const void* const* arena_base, const int* buffer, const int32_t* const* kv_len_dev,
+                                int n_streams, int layer, const void* q, void* out, int q_heads, int kv_len, int num_splits,
+                                void* workspace, float scale, cudaStream_t st) {
+    const int D = geom->head_dim, H = geom->kv_heads, G = q_heads / H;
+    ArenaDims ad{geom->layers, H, D, geom->capacity};
+    static thread_local DecMaps maps;
     int rc;
     {
-        uint64_t dims[3] = {(uint64_t)D, (uint64_t)q_heads, 1};
+        uint64_t dims[3] = {(uint64_t)D, (uint64_t)q_heads, (uint64_t)n_streams};
         uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)q_heads * D * 2};
         uint32_t box[3] = {64, 16, 1};
-        if ((rc = make_tensor_map_bf16(&tq, q, 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&maps.q, q, 3, dims, str, box, 1))) return rc;
     }
-    {
+    DecParams p{};
+    for (int b = 0; b < n_streams; ++b) {
+        const uint16_t* base = (const uint16_t*)arena_base[b];
         uint64_t dims[3] = {(uint64_t)D, (uint64_t)ad.cap, (uint64_t)ad.L * H};
         uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)ad.cap * D * 2};
         uint32_t box[3] = {64, DEC_BN, 1};
-        if ((rc = make_tensor_map_bf16(&tk, base + ad.offset(buffer, SVLM_PLANE_K_ROT, 0, 0, 0), 3, dims, str, box, 1))) return rc;
-        if ((rc = make_tensor_map_bf16(&tv, base + ad.offset(buffer, SVLM_PLANE_V, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&maps.k[b], base + ad.offset(buffer[b], SVLM_PLANE_K_ROT, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+        if ((rc = make_tensor_map_bf16(&maps.v[b], base + ad.offset(buffer[b], SVLM_PLANE_V, 0, 0, 0), 3, dims, str, box, 1))) return rc;
+        p.kv_len_dev[b] = kv_len_dev[b];
     }
-    DecParams p{};
     p.Hq = q_heads; p.G = G; p.D = D;
-    p.kv_len = kv_len; p.kv_len_dev = kv_len_dev; p.num_splits = num_splits;
+    p.kv_len = kv_len; p.num_splits = num_splits;
+    p.rows_total = n_streams * q_heads;
     p.kv_head_base = layer * H;
     p.out = (uint16_t*)out;
     p.part_o = (float*)workspace;
-    p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + (size_t)num_splits * q_heads * D) : nullptr;
+    p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + (size_t)num_splits * p.rows_total * D) : nullptr;
     p.scale_log2 = scale * 1.4426950408889634f;
 #ifdef SVLM_TRACE
     p.trace = (unsigned long long*)getenv_ptr("SVLM_TRACE_PTR");
 #endif
-    if ((rc = launch_decode_g(G, tq, tk, tv, p, dim3(num_splits, H), st))) return rc;
+    if ((rc = launch_decode_g(G, maps, p, dim3(num_splits, H, n_streams), st))) return rc;
     if (num_splits > 1) {
         // A separate merge launch beats an in-kernel "last CTA merges" epilogue here (measured: 10.2 vs 12.6 us per layer at
-        // 4k keys, 30.1 vs 33.7 us at 64k): 28 one-head CTAs finish the merge in one load latency.
-        launch_pdl(attn_combine_kernel, dim3(q_heads), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out, q_heads, D, num_splits);
+        // 4k keys, 30.1 vs 33.7 us at 64k): one-head CTAs finish the merge in one load latency.
+        launch_pdl(attn_combine_kernel, dim3(p.rows_total), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out,
+                   p.rows_total, D, num_splits);
         return launch_status("attn_combine_kernel");
     }
     return SVLM_OK;
 }
 
+int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
+                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st) {
+    const void* base = arena->base;
+    return decode_launch_common(arena, &base, &buffer, &kv_len_dev, 1, layer, q, out, q_heads, kv_len, num_splits, workspace, scale, st);
+}
+
 }  // namespace svlm
+
+using namespace svlm;
+
+extern "C" int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
+                                        const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
+                                        size_t workspace_bytes, float scale, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(geometry && slots && q && out, "NULL argument");
+    SVLM_REQUIRE(geometry->layers > 0 && geometry->kv_heads > 0 && geometry->capacity > 0 && geometry->head_dim == 128, "bad arena geometry");
+    SVLM_REQUIRE(n_streams >= 1 && n_streams <= SVLM_MAX_STREAMS, "n_streams %d out of range (1..%d)", n_streams, SVLM_MAX_STREAMS);
+    SVLM_REQUIRE(layer >= 0 && layer < geometry->layers, "layer %d out of range", layer);
+    SVLM_REQUIRE(q_heads > 0 && q_heads % geometry->kv_heads == 0 && q_heads / geometry->kv_heads <= 8,
+                 "q_heads %d must be 1..8 times kv_heads %d", q_heads, geometry->kv_heads);
+    SVLM_REQUIRE(max_kv_len >= 1 && max_kv_len <= geometry->capacity, "max_kv_len %d out of range", max_kv_len);
+    SVLM_REQUIRE(num_splits >= 1 && num_splits <= 256, "num_splits %d out of range", num_splits);
+    SVLM_REQUIRE((((uintptr_t)q | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0, "q/out/workspace must be 16-byte aligned");
+    const size_t rows = (size_t)num_splits * n_streams * q_heads;
+    const size_t need = num_splits > 1 ? rows * geometry->head_dim * sizeof(float) + rows * sizeof(float2) : 0;
+    SVLM_REQUIRE(num_splits == 1 || (workspace != nullptr && workspace_bytes >= need), "workspace too small: need %zu bytes", need);
+    const void* base[SVLM_MAX_STREAMS];
+    int buffer[SVLM_MAX_STREAMS];
+    const int32_t* kvl[SVLM_MAX_STREAMS];
+    for (int b = 0; b < n_streams; ++b) {
+        SVLM_REQUIRE(slots[b].arena_base && slots[b].kv_len_dev, "slot %d: NULL pointer", b);
+        SVLM_REQUIRE(slots[b].buffer == 0 || slots[b].buffer == 1, "slot %d: buffer must be 0 or 1", b);
+        SVLM_REQUIRE(((uintptr_t)slots[b].arena_base & 127) == 0, "slot %d: arena must be 128-byte aligned", b);
+        base[b] = slots[b].arena_base; buffer[b] = slots[b].buffer; kvl[b] = slots[b].kv_len_dev;
+    }
+    return decode_launch_common(geometry, base, buffer, kvl, n_streams, layer, q, out, q_heads, max_kv_len, num_splits, workspace, scale,
+                                (cudaStream_t)stream);
+}

@@ -276,6 +276,58 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(uint16_t* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// qkv_rope_append for the decode step of several streams: CTA b appends token b to the arena of stream b at the row and
+// text position its device-side counters name.  Same arithmetic as qkv_rope_append_kernel.
+// ---------------------------------------------------------------------------------------------------
+struct AppendSlots {
+    uint16_t* buf[SVLM_MAX_STREAMS];            // live buffer of each stream's arena
+    const int32_t* row[SVLM_MAX_STREAMS];
+    const int32_t* pos[SVLM_MAX_STREAMS];
+};
+
+__global__ void __launch_bounds__(256) qkv_rope_append_streams_kernel(const AppendSlots sl, ArenaDims ad, int layer,
+                                                                       const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                                       const uint16_t* __restrict__ v, int64_t qs, int64_t ks, int64_t vs,
+                                                                       int hq, uint16_t* __restrict__ q_out, RopeTables tab) {
+    const int t = blockIdx.x;
+    const int lane16 = threadIdx.x & 15;
+    const int hw = threadIdx.x >> 4;
+    const int jj = lane16 & 7;
+    const bool first_half = lane16 < 8;
+    const int row = __ldg(sl.row[t]);
+    if (row < 0 || row >= ad.cap) return;
+    const int p = min(max(__ldg(sl.pos[t]), 0), tab.rows - 1);
+    const uint4 c = __ldg(tab.cos + (int64_t)p * 8 + jj);
+    const uint4 s = __ldg(tab.sin + (int64_t)p * 8 + jj);
+    const int64_t plane = ad.plane_elems();
+    uint16_t* buf = sl.buf[t];
+    const int n_rows = hq + 2 * ad.H;
+    const int iters = (n_rows + 15) / 16;
+    for (int it = 0; it < iters; ++it) {
+        const int r = it * 16 + hw;
+        const bool valid = r < n_rows;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            const uint16_t* srcp = r < hq ? q + t * qs + (int64_t)r * ad.D
+                                 : (r < hq + ad.H ? k + t * ks + (int64_t)(r - hq) * ad.D : v + t * vs + (int64_t)(r - hq - ad.H) * ad.D);
+            x = *reinterpret_cast<const uint4*>(srcp + lane16 * 8);
+        }
+        const uint4 partner = shfl_xor_u4(x, 8);
+        if (!valid) continue;
+        if (r < hq) {
+            *reinterpret_cast<uint4*>(q_out + ((int64_t)t * hq + r) * ad.D + lane16 * 8) = rope_chunk(x, partner, c, s, first_half);
+        } else if (r < hq + ad.H) {
+            const int64_t o = (((int64_t)layer * ad.H + (r - hq)) * ad.cap + row) * ad.D + lane16 * 8;
+            *reinterpret_cast<uint4*>(buf + SVLM_PLANE_K_RAW * plane + o) = x;
+            *reinterpret_cast<uint4*>(buf + SVLM_PLANE_K_ROT * plane + o) = rope_chunk(x, partner, c, s, first_half);
+        } else {
+            const int64_t o = (((int64_t)layer * ad.H + (r - hq - ad.H)) * ad.cap + row) * ad.D + lane16 * 8;
+            *reinterpret_cast<uint4*>(buf + SVLM_PLANE_V * plane + o) = x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // vit_rope: qkv [N][3][H][D] bf16, q and k rotated in place.  fp32 products and sum, no FMA contraction
 // (apply_rotary_pos_emb_flashatt semantics: q.float()*cos + rotate_half(q.float())*sin, cast back).
 // One thread = one 8-element chunk of the first half and its partner chunk in the second half.
@@ -481,6 +533,36 @@ extern "C" int svlm_qkv_rope_append(const svlm_arena_t* arena, int buffer, int l
         (uint16_t*)arena->base, ad, buffer, layer, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, q_row_stride, k_row_stride,
         v_row_stride, q_heads, (uint16_t*)q_out, start, start_dev, pos, pos_stride, text_pos_dev, tab);
     return launch_status("qkv_rope_append_kernel");
+}
+
+extern "C" int svlm_qkv_rope_append_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
+                                            const void* q, const void* k, const void* v, int64_t q_row_stride, int64_t k_row_stride,
+                                            int64_t v_row_stride, int q_heads, void* q_out, const void* cos_table, const void* sin_table,
+                                            int table_rows, const int32_t* mrope_section_host, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(geometry && slots, "NULL geometry / slots");
+    SVLM_REQUIRE(geometry->layers > 0 && geometry->kv_heads > 0 && geometry->capacity > 0 && geometry->head_dim == 128, "bad arena geometry");
+    SVLM_REQUIRE(n_streams >= 1 && n_streams <= SVLM_MAX_STREAMS, "n_streams %d out of range (1..%d)", n_streams, SVLM_MAX_STREAMS);
+    SVLM_REQUIRE(layer >= 0 && layer < geometry->layers, "layer %d out of range", layer);
+    SVLM_REQUIRE(q && k && v && q_out && cos_table && sin_table, "NULL tensor argument");
+    SVLM_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)q_out) & 15) == 0, "q/k/v/q_out must be 16-byte aligned");
+    SVLM_REQUIRE(q_row_stride % 8 == 0 && k_row_stride % 8 == 0 && v_row_stride % 8 == 0, "row strides must be multiples of 8 elements");
+    RopeTables tab;
+    if ((rc = make_tables(&tab, cos_table, sin_table, table_rows, mrope_section_host, geometry->head_dim))) return rc;
+    ArenaDims ad{geometry->layers, geometry->kv_heads, geometry->head_dim, geometry->capacity};
+    AppendSlots sl{};
+    for (int b = 0; b < n_streams; ++b) {
+        SVLM_REQUIRE(slots[b].arena_base && slots[b].row_dev && slots[b].pos_dev, "slot %d: NULL pointer", b);
+        SVLM_REQUIRE(slots[b].buffer == 0 || slots[b].buffer == 1, "slot %d: buffer must be 0 or 1", b);
+        sl.buf[b] = (uint16_t*)slots[b].arena_base + (int64_t)slots[b].buffer * ad.buffer_elems();
+        sl.row[b] = slots[b].row_dev;
+        sl.pos[b] = slots[b].pos_dev;
+    }
+    qkv_rope_append_streams_kernel<<<n_streams, 256, 0, (cudaStream_t)stream>>>(sl, ad, layer, (const uint16_t*)q, (const uint16_t*)k,
+                                                                                (const uint16_t*)v, q_row_stride, k_row_stride,
+                                                                                v_row_stride, q_heads, (uint16_t*)q_out, tab);
+    return launch_status("qkv_rope_append_streams_kernel");
 }
 
 extern "C" int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int n_tokens, int heads, int head_dim, void* stream) {

@@ -412,3 +412,93 @@ def test_gemv_qkv_rope_append_matches_unfused(abi, tables):
     untouched[77] = False
     assert torch.equal(bits(a2[:, :, :, :, untouched].cpu()), bits(a1[:, :, :, :, untouched].cpu()))
     assert torch.equal(bits(a2[:, :, 0].cpu()), bits(a1[:, :, 0].cpu())), "other layers untouched"
+
+
+# ------------------------------------------------------------------------------------------------ several streams per launch
+class _FakeCache:
+    """The two attributes `_abi.make_slots` reads from a StreamingCache."""
+
+    def __init__(self, arena, cur):
+        self.arena, self.cur = arena, cur
+
+
+def _stream_setup(abi, n_streams, L, H, cap, kv_lens, curs):
+    arenas, caches = [], []
+    for b in range(n_streams):
+        cpu, dev, _ = make_arena(abi, L, H, cap, seed=50 + b)
+        dev[1].copy_(dev[0])
+        arenas.append((cpu, dev))
+        caches.append(_FakeCache(dev, curs[b]))
+    rows = [torch.tensor([n], dtype=torch.int32, device=DEV) for n in kv_lens]
+    after = [torch.tensor([n + 1], dtype=torch.int32, device=DEV) for n in kv_lens]
+    pos = [torch.tensor([1000 + 17 * b], dtype=torch.int32, device=DEV) for b in range(n_streams)]
+    return arenas, caches, rows, after, pos
+
+
+@pytest.mark.gpu
+def test_qkv_rope_append_streams_matches_single_stream(abi, tables):
+    """Token b lands in stream b's arena exactly as the single-stream append would put it; nothing else is touched."""
+    B, L, H, cap, Hq = 3, 2, 2, 512, 4
+    kv_lens, curs = [200, 37, 511], [1, 0, 1]
+    arenas, caches, rows, after, pos = _stream_setup(abi, B, L, H, cap, kv_lens, curs)
+    ref = [a[1].clone() for a in arenas]
+    g = torch.Generator().manual_seed(8)
+    qkv = torch.randn(B, (Hq + 2 * H) * 128, generator=g).to(torch.bfloat16).to(DEV)
+    q, k, v = qkv[:, :Hq * 128], qkv[:, Hq * 128:(Hq + H) * 128], qkv[:, (Hq + H) * 128:]
+    cos, sin = (t.to(DEV) for t in tables)
+    layer = 1
+    q_ref = torch.zeros(B, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    for b in range(B):
+        abi.qkv_rope_append(abi.ArenaView(ref[b]), curs[b], layer, q[b:b + 1], k[b:b + 1], v[b:b + 1], 1, Hq, q_ref[b:b + 1], 0, None,
+                            cos, sin, SECTION, start_dev=rows[b], text_pos_dev=pos[b])
+    q_out = torch.zeros(B, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    slots = abi.make_slots(caches, rows, pos, after)
+    abi.qkv_rope_append_streams(abi.ArenaView(arenas[0][1]), slots, layer, q, k, v, Hq, q_out, cos, sin, SECTION)
+    torch.cuda.synchronize()
+    assert torch.equal(bits(q_out.cpu()), bits(q_ref.cpu()))
+    for b in range(B):
+        assert torch.equal(bits(arenas[b][1].cpu()), bits(ref[b].cpu())), f"stream {b}"
+        assert not torch.equal(bits(arenas[b][1].cpu()), bits(arenas[b][0]))       # the row really was written
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,kv_lens,splits", [(3, [300, 5343, 129], 8), (8, [5789, 5700, 4100, 128, 1, 6000, 5789, 2500], 16),
+                                              (2, [1000, 77], 1)])
+def test_attn_decode_streams_matches_single_stream(abi, B, kv_lens, splits):
+    """One launch over B streams == B single-stream launches, bit for bit (same kernel, same split boundaries per stream)."""
+    Hq, H, L = 28, 4, 2
+    cap = 6144
+    curs = [b & 1 for b in range(B)]
+    arenas, caches, rows, after, pos = _stream_setup(abi, B, L, H, cap, kv_lens, curs)
+    kv = [torch.tensor([n], dtype=torch.int32, device=DEV) for n in kv_lens]
+    q = torch.randn(B, Hq, 128, generator=torch.Generator().manual_seed(B)).to(torch.bfloat16).to(DEV)
+    layer, scale = 1, 1.0 / math.sqrt(128)
+    ws1 = torch.zeros(abi.attn_workspace_bytes(1, Hq, 128, splits) // 4 + 16, dtype=torch.float32, device=DEV) if splits > 1 else None
+    ref = torch.zeros(B, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    for b in range(B):
+        abi.attn_causal(abi.ArenaView(arenas[b][1]), curs[b], layer, q[b:b + 1], ref[b:b + 1], 1, Hq, cap, scale, splits, ws1, kv_len_dev=kv[b])
+    wsB = torch.zeros(abi.attn_workspace_bytes(B, Hq, 128, splits) // 4 + 16, dtype=torch.float32, device=DEV) if splits > 1 else None
+    out = torch.zeros(B, Hq, 128, dtype=torch.bfloat16, device=DEV)
+    slots = abi.make_slots(caches, rows, pos, kv)
+    abi.attn_decode_streams(abi.ArenaView(arenas[0][1]), slots, layer, q, out, Hq, cap, scale, splits, wsB)
+    torch.cuda.synchronize()
+    assert torch.equal(bits(out.cpu()), bits(ref.cpu()))
+    # and against the definition for one of the streams
+    b = 0
+    cpu = arenas[b][0]
+    want = o_attn.attention(q[b:b + 1].cpu().transpose(0, 1), cpu[0, 1, layer, :, :kv_lens[b]], cpu[0, 2, layer, :, :kv_lens[b]], causal=True)
+    torch.testing.assert_close(out[b].cpu().float().reshape(1, -1), want.float(), **ATT_TOL)
+
+
+@pytest.mark.gpu
+def test_streams_argument_errors(abi):
+    cpu, dev, view = make_arena(abi, 1, 2, 256, seed=3)
+    one = torch.zeros(1, dtype=torch.int32, device=DEV)
+    q = torch.zeros(9, 4, 128, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(ValueError):
+        abi.make_slots([_FakeCache(dev, 0)] * 9, [one] * 9, [one] * 9, [one] * 9)
+    slots = abi.make_slots([_FakeCache(dev, 0)], [one], [one], [one])
+    with pytest.raises(RuntimeError, match="workspace"):
+        abi.attn_decode_streams(view, slots, 0, q[:1], q[:1].clone(), 4, 256, 0.1, 4, None)
+    with pytest.raises(RuntimeError, match="layer"):
+        abi.attn_decode_streams(view, slots, 5, q[:1], q[:1].clone(), 4, 256, 0.1, 1, None)
