@@ -91,7 +91,7 @@ class StreamingEngine:
     def __init__(self, weights: dict, geo: Geometry, capacity: int = 8192, device="cuda", window_size=DEFAULT_WINDOW_SIZE,
                  text_round=DEFAULT_TEXT_ROUND, text_sink=DEFAULT_TEXT_SINK, text_sliding_window=DEFAULT_TEXT_SLIDING_WINDOW,
                  max_new_tokens=MAX_TOKEN_PER_DURATION, suppress=None, assistant_start_bias=3, assistant_end_bias=2,
-                 use_graph=True, decode_splits=None, prefill_splits=None):
+                 use_graph=True, decode_splits=None, prefill_splits=None, share_weights_from=None):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         _abi.lib()
@@ -106,7 +106,11 @@ class StreamingEngine:
         self.scale = 1.0 / math.sqrt(geo.head_dim)
         self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 296 // geo.num_kv_heads))   # two CTAs per SM
         self.prefill_splits = prefill_splits
-        self._prepare_weights(weights)
+        if share_weights_from is not None:      # another stream of the same model on this GPU: one copy of the weights
+            for name in ("w_patch", "vit", "vit_mlp_padded", "merger", "embed", "layers", "norm", "lm_head"):
+                setattr(self, name, getattr(share_weights_from, name))
+        else:
+            self._prepare_weights(weights)
         g = geo
         dev = self.device
         self.ws = torch.zeros(max(_abi.attn_workspace_bytes(1, g.num_heads, g.head_dim, self.decode_splits),
@@ -489,12 +493,10 @@ class StreamingEngine:
         c.compact([(0, 0, n)], self.prev_ids[:n])
 
     # ------------------------------------------------------------------ session loop (inference.py:309-517)
-    def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None):
+    def begin_step(self, prompt_ids, grid, previous_text=""):
+        """Eviction half of a chunk (`process_past_kv` + position recompute, inference.py:309-420): plans the pruning of the
+        previous ids, compacts + re-rotates the arena, uploads ids and positions.  Returns (ids of this chunk, gather runs)."""
         i, c = self.i, self.cache
-        if sync_timing:
-            torch.cuda.synchronize()
-        self._mark("step_start")
-        t0 = time.perf_counter()
         runs, plan = None, None
         if self.prev_ids is not None:
             plan = plan_past_kv(self.prev_ids, i, self.text_round, self.window_size, self.history, self.asb, self.aeb,
@@ -524,6 +526,26 @@ class StreamingEngine:
         if runs is not None and not (len(runs) == 1 and runs[0] == (0, 0, c.seq_len)):
             c.compact(runs)
             self.launches += 1
+        return ids, runs
+
+    def finish_step(self, ids, seq, runs, t_pkv=0.0, t_gen=0.0, n_fwd=0):
+        """Bookkeeping after generation (inference.py:457-517): close the turn, remember the ids, extend the history."""
+        input_len = len(ids)
+        if seq[-1] != IM_END:
+            seq.append(IM_END)
+        new_tokens = seq[input_len:]
+        self.prev_ids = np.asarray(seq, dtype=np.int64)
+        self.history.append({"role": "assistant", "content": " ".join(str(t) for t in new_tokens) + " ..."})
+        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens)})
+        self.i += 1
+        return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "runs": runs, "cache_len": self.cache.seq_len}
+
+    def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None):
+        if sync_timing:
+            torch.cuda.synchronize()
+        self._mark("step_start")
+        t0 = time.perf_counter()
+        ids, runs = self.begin_step(prompt_ids, grid, previous_text)
         if sync_timing:
             torch.cuda.synchronize()
         t_pkv = time.perf_counter() - t0
@@ -533,12 +555,4 @@ class StreamingEngine:
         if sync_timing:
             torch.cuda.synchronize()
         t_gen = time.perf_counter() - t0
-        input_len = len(ids)
-        if seq[-1] != IM_END:
-            seq.append(IM_END)
-        new_tokens = seq[input_len:]
-        self.prev_ids = np.asarray(seq, dtype=np.int64)
-        self.history.append({"role": "assistant", "content": " ".join(str(t) for t in new_tokens) + " ..."})
-        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd, "new_tokens": len(new_tokens)})
-        self.i += 1
-        return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "runs": runs, "cache_len": c.seq_len}
+        return self.finish_step(ids, seq, runs, t_pkv, t_gen, n_fwd)

@@ -69,8 +69,14 @@ class StreamingCache:
         self.layers, self.kv_heads, self.head_dim = geo.num_layers, geo.num_kv_heads, geo.head_dim
         self.capacity = int(capacity)
         self.device = torch.device(device)
-        self.arena = torch.zeros(2, 3, self.layers, self.kv_heads, self.capacity, self.head_dim, dtype=torch.bfloat16,
-                                 device=self.device)
+        # The TMA / UMMA tiles want a 1024-byte aligned base; torch's caching allocator only promises 512 bytes.
+        shape = (2, 3, self.layers, self.kv_heads, self.capacity, self.head_dim)
+        n_el = 1
+        for d in shape:
+            n_el *= d
+        self._arena_storage = torch.zeros(n_el + 512, dtype=torch.bfloat16, device=self.device)
+        skip = (-self._arena_storage.data_ptr() % 1024) // 2
+        self.arena = self._arena_storage[skip:skip + n_el].view(shape)
         self.view = _abi.ArenaView(self.arena)
         self.cur = 0
         self.seq_len = 0

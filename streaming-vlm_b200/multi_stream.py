@@ -1,0 +1,189 @@
+"""Several independent streams on ONE GPU ("one or more streams per GPU", BASELINE config 4).
+
+The reference runs one stream per process (`eval/livesports3kcc/distributed_generate_streaming.py:53-62`): every
+stream pays its own sweep of the 15 GB of weights for every decoded token.  Streams are independent, but the weights
+are not: here the streams keep their own session state, K/V arena and eviction schedule (one `StreamingEngine` each,
+sharing one copy of the weights), the eviction / ViT / chunk prefill of each stream run exactly as in the single-stream
+engine, and the DECODE steps of all streams advance together:
+
+* dense projections see a `[B, hidden]` activation matrix -- one weight sweep for B tokens (cuBLAS: a plain library
+  GEMM; the M = 1 GEMV kernels of the single-stream path do not apply);
+* `svlm_qkv_rope_append_streams` appends token b to stream b's arena at that stream's row / text position;
+* `svlm_attn_decode_streams` is one split-KV launch over all streams (grid = splits x kv heads x streams): B x the bytes
+  of a single-stream decode attention per launch, which is what lifts it from latency-bound to HBM-bound;
+* each step is one CUDA-graph replay; per-stream kv length, next position, token and an `active` flag live in
+  device memory, so streams that finished their turn (EOS / token budget) simply stop advancing.
+
+Results per stream are those of the single-stream engine up to the GEMM-vs-GEMV rounding of the decode projections
+(`tests/test_gpu_multistream.py`).
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import _abi
+from .config import Geometry
+from .engine import IM_END, StreamingEngine
+
+
+class MultiStreamEngine:
+    def __init__(self, weights: dict, geo: Geometry, n_streams: int, capacity: int = 8192, device="cuda", **engine_kwargs):
+        if not 1 <= n_streams <= _abi.MAX_STREAMS:
+            raise ValueError(f"1..{_abi.MAX_STREAMS} streams per engine, got {n_streams}")
+        first = StreamingEngine(weights, geo, capacity, device, **engine_kwargs)
+        self.engines = [first] + [StreamingEngine(None, geo, capacity, device, share_weights_from=first, **engine_kwargs)
+                                  for _ in range(n_streams - 1)]
+        self.geo, self.device, self.n = geo, first.device, n_streams
+        dev, B = self.device, n_streams
+        # device-side counters of all streams, one tensor each; the engines' own scalars become views of them
+        self.kv_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.kv_after = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.next_pos = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.tok = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.active = torch.zeros(B, dtype=torch.int32, device=dev)
+        for b, e in enumerate(self.engines):
+            e.kv_len_dev, e.kv_after_dev = self.kv_len[b:b + 1], self.kv_after[b:b + 1]
+            e.tok_dev, e.cache.next_pos = self.tok[b:b + 1], self.next_pos[b:b + 1]
+        self._tok_pinned = torch.zeros(B, dtype=torch.int64).pin_memory()
+        self._active_pinned = torch.zeros(B, dtype=torch.int32).pin_memory()
+        g = geo
+        self._q_rot = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+        self._o = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+        # enough CTAs for two per SM, ~3 key tiles per CTA (see StreamingEngine.decode_step)
+        self.max_splits = max(1, min((capacity + 127) // 128, -(-592 // (g.num_kv_heads * B))))
+        self.ws = torch.zeros(_abi.attn_workspace_bytes(B, g.num_heads, g.head_dim, self.max_splits) // 4 + 16, dtype=torch.float32,
+                              device=dev)
+        self._graphs, self._slots = {}, {}
+        self.use_graph = first.use_graph
+        self.launches = 0
+        self.timing = []
+
+    # ------------------------------------------------------------------ batched decode step
+    def _decode_body(self, slots, splits):
+        e0, g, B = self.engines[0], self.geo, self.n
+        hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
+        c0 = e0.cache
+        before = e0.launches
+        x = F.embedding(self.tok, e0.embed)
+        pending = None
+        for li, L in enumerate(e0.layers):
+            x, h = e0._add_norm(x, pending, L["ln1"], g.rms_eps)
+            qkv = F.linear(h, L["wqkv"], L["bqkv"])
+            q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+            _abi.qkv_rope_append_streams(c0.view, slots, li, q, k, v, hq, self._q_rot, c0.cos_table, c0.sin_table, c0.section)
+            _abi.attn_decode_streams(c0.view, slots, li, self._q_rot, self._o, hq, c0.capacity, e0.scale, splits,
+                                     self.ws if splits > 1 else None)
+            x, h = e0._add_norm(x, F.linear(self._o.view(B, -1), L["wo"]), L["ln2"], g.rms_eps)
+            pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
+        logits = e0._logits(x, pending)                                   # [B, vocab] fp32, suppressed ids at -inf
+        nxt = torch.argmax(logits, dim=-1)
+        act = self.active
+        self.tok.copy_(torch.where(act.bool(), nxt, self.tok))
+        self.kv_len.add_(act)
+        self.kv_after.copy_(self.kv_len + 1)
+        self.next_pos.add_(act)
+        self.launches += (e0.launches - before) + g.num_layers * (2 + (1 if splits > 1 else 0))
+        e0.launches = before
+
+    def decode_step(self):
+        """Every ACTIVE stream consumes its token in `self.tok`, appends its K/V and leaves its next greedy token there."""
+        caches = [e.cache for e in self.engines]
+        n_tiles = max(c.seq_len for c in caches) // 128 + 1
+        splits = max(1, min(self.max_splits, -(-n_tiles // 3)))
+        key = (tuple(c.cur for c in caches), splits)
+        slots = self._slots.get(key[0])
+        if slots is None:
+            slots = self._slots[key[0]] = _abi.make_slots(caches, list(self.kv_len.split(1)), list(self.next_pos.split(1)),
+                                                          list(self.kv_after.split(1)))
+        if not self.use_graph:
+            self._decode_body(slots, splits)
+            return
+        entry = self._graphs.get(key)
+        if entry is None:
+            saved = [t.clone() for t in (self.kv_len, self.kv_after, self.next_pos, self.tok)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._decode_body(slots, splits)                           # warm-up outside capture (cuBLAS workspaces)
+            torch.cuda.current_stream().wait_stream(side)
+            for t, s in zip((self.kv_len, self.kv_after, self.next_pos, self.tok), saved):
+                t.copy_(s)
+            torch.cuda.synchronize()
+            before = self.launches
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._decode_body(slots, splits)
+            entry = self._graphs[key] = (gr, self.launches - before)
+            self.launches = before
+        entry[0].replay()
+        self.launches += entry[1]
+
+    # ------------------------------------------------------------------ one chunk of every stream
+    def step(self, prompts, pixels, grid, previous_text="", forced=None, sync_timing=True):
+        """One chunk for each stream (`prompts[b]`, `pixels[b]`; same grid).  `forced[b]`: teacher-forced tokens of stream b
+        (see StreamingEngine.generate).  Returns the per-stream result dicts of StreamingEngine.step."""
+        B, engines = self.n, self.engines
+        if sync_timing:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids_all, runs_all = [], []
+        for b, e in enumerate(engines):
+            ids, runs = e.begin_step(prompts[b], grid, previous_text)
+            ids_all.append(ids)
+            runs_all.append(runs)
+        if sync_timing:
+            torch.cuda.synchronize()
+        t_pkv = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for b, e in enumerate(engines):
+            c = e.cache
+            video = e.vision_forward(pixels[b], grid) if pixels[b] is not None else None
+            logits = e.prefill(ids_all[b][c.seq_len:], video)
+            e.tok_dev.copy_(torch.argmax(logits, dim=-1))
+            e.kv_len_dev.fill_(c.seq_len)
+            e.kv_after_dev.fill_(c.seq_len + 1)
+        seqs = [list(ids) for ids in ids_all]
+        done = [False] * B
+        argmaxes = [[] for _ in range(B)]
+        self.active.fill_(1)
+        n_fwd = 1
+        while True:
+            self._tok_pinned.copy_(self.tok, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            changed = False
+            for b in range(B):
+                if done[b]:
+                    continue
+                tok = int(self._tok_pinned[b])
+                argmaxes[b].append(tok)
+                f = None if forced is None else forced[b]
+                if f is not None and len(argmaxes[b]) <= len(f) and f[len(argmaxes[b]) - 1] != tok:
+                    tok = int(f[len(argmaxes[b]) - 1])
+                    engines[b].tok_dev.fill_(tok)
+                seqs[b].append(tok)
+                if tok == IM_END or len(seqs[b]) - len(ids_all[b]) >= engines[b].max_new_tokens:
+                    done[b] = changed = True
+            if all(done):
+                break
+            if changed:
+                for b in range(B):
+                    self._active_pinned[b] = 0 if done[b] else 1
+                self.active.copy_(self._active_pinned, non_blocking=True)
+            self.decode_step()
+            n_fwd += 1
+            for b, e in enumerate(engines):
+                if not done[b]:
+                    e.cache.seq_len += 1
+                    e.cache._seen_tokens += 1
+        if sync_timing:
+            torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        self.last_argmax = argmaxes
+        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "n_forward": n_fwd})
+        return [e.finish_step(ids_all[b], seqs[b], runs_all[b], t_pkv / B, t_gen / B, n_fwd) for b, e in enumerate(engines)]
+
+    def total_launches(self):
+        return self.launches + sum(e.launches for e in self.engines)

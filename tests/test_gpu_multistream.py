@@ -1,0 +1,68 @@
+"""GPU parity of the multi-stream engine (several streams per GPU, BASELINE config 4 at one GPU): B tiny-model streams
+with different frames and prompt lengths advance through ONE batched decode step per token; each stream is checked
+against its own CPU oracle session exactly like the single-stream test (`tests/test_gpu_session.py`): pruned ids, gather
+runs and cache lengths bit-exact, greedy ids identical up to oracle near-ties (teacher-forced)."""
+import pytest
+import torch
+
+from oracle.model import Session
+from streaming_vlm_b200 import synthetic
+from streaming_vlm_b200.config import TINY
+from tests.stream_sim import rle
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.08
+
+
+def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, use_graph=True):
+    from streaming_vlm_b200.multi_stream import MultiStreamEngine
+    geo = TINY
+    w_cpu = synthetic.random_weights(geo, seed=0)
+    suppress = synthetic.suppress_mask(geo.vocab)
+    oracles = [Session(w_cpu, geo.as_dict(), window, text_round, sink, sliding, suppress=suppress) for _ in range(n_streams)]
+    multi = MultiStreamEngine({k: v.clone() for k, v in w_cpu.items()}, geo, n_streams, capacity=4096, window_size=window,
+                              text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress, use_graph=use_graph)
+    n_vis = (height // 28) * (width // 28)
+    mismatches = total = 0
+    prev_len = [0] * n_streams
+    for i in range(n_chunks):
+        prompts, pixels, ros = [], [], []
+        for b in range(n_streams):
+            px, grid = synthetic.patchify(synthetic.frames(1000 * b + i, height, width), geo)
+            prompt = synthetic.round_prompt(i, n_vis, 4 + 3 * b)          # different previous-text lengths per stream
+            ros.append(oracles[b].step(prompt, px.to(torch.bfloat16), grid))
+            prompts.append(prompt)
+            pixels.append(px.to("cuda"))
+        rgs = multi.step(prompts, pixels, grid, forced=[r["new_tokens"] for r in ros])
+        for b, (rg, ro) in enumerate(zip(rgs, ros)):
+            assert rg["ids"] == ro["ids"], f"chunk {i} stream {b}: ids"
+            assert rg["input_len"] == ro["input_len"] and rg["cache_len"] == ro["cache_len"], f"chunk {i} stream {b}"
+            if ro["gather"] is not None:
+                want = [x for x in ro["gather"] if x < prev_len[b]]
+                got = [s_ + k for s_, _, l in rg["runs"] for k in range(l)]
+                assert got == want, f"chunk {i} stream {b}: gather {rle(got)} vs {rle(want)}"
+            prev_len[b] = ro["cache_len"]
+            for j, (tg, to) in enumerate(zip(multi.last_argmax[b], ro["new_tokens"])):
+                total += 1
+                if tg != to:
+                    mismatches += 1
+                    lo = ro["step_logits"][j]
+                    assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} stream {b} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]}"
+    return mismatches, total, multi
+
+
+def test_three_streams_small_windows():
+    mism, total, multi = _run(3, 12, 112, 112, 4, 4, 16, 24)
+    assert all(e.cache.compactions >= 6 for e in multi.engines)
+    assert len({tuple(e.prev_ids.tolist()) for e in multi.engines}) == 3          # the streams really differ
+    assert mism <= max(2, total // 20), (mism, total)
+
+
+def test_two_streams_eager_equals_graph():
+    """The CUDA-graph replay of the batched step and its eager execution produce the same tokens."""
+    _, _, a = _run(2, 6, 112, 112, 4, 4, 16, 24, use_graph=True)
+    _, _, b = _run(2, 6, 112, 112, 4, 4, 16, 24, use_graph=False)
+    for ea, eb in zip(a.engines, b.engines):
+        assert ea.prev_ids.tolist() == eb.prev_ids.tolist()
+        assert ea.cache.seq_len == eb.cache.seq_len
