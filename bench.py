@@ -282,6 +282,80 @@ def kernel_rooflines(engine, pk):
     return out
 
 
+def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
+    """BASELINE configs[3] at this GPU: `n_streams` independent 7B streams sharing the GPU (and one copy of the weights), each
+    in the same steady state as the headline stream but with its own frames, prompts and cache contents.  One ROUND = one
+    chunk of every stream (per-stream eviction, ViT and prefill, then batched decode steps).  Pixel values resident in HBM."""
+    from streaming_vlm_b200 import _abi, synthetic
+    from streaming_vlm_b200.config import QWEN25VL_7B as G7
+    from streaming_vlm_b200.multi_stream import MultiStreamEngine
+    multi = MultiStreamEngine(None, G7, n_streams, capacity=8192, device=dev, suppress=synthetic.suppress_mask(G7.vocab),
+                              share_weights_from=engine)
+    total = warmup + rounds
+    prompts, pixels = [], []
+    grid = None
+    for b, e in enumerate(multi.engines):
+        seed = 1000 * rank + 100 + b
+        e.load_state(synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS, seed=seed), seed=seed)
+    base_i = multi.engines[0].i
+    for k in range(total):
+        pr, px = [], []
+        for b in range(n_streams):
+            p_, grid = synthetic.patchify(synthetic.frames(7919 * (b + 1) + base_i + k), G7, dtype=torch.float32)
+            px.append(p_.to(dev))
+            pr.append(synthetic.round_prompt(base_i + k, seed=1000 * rank + 100 + b))
+        prompts.append(pr)
+        pixels.append(px)
+    toks = 0
+    for k in range(warmup):
+        multi.step(prompts[k], pixels[k], grid, sync_timing=False)
+    torch.cuda.synchronize()
+    l0 = multi.total_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_fwd = 0
+    for k in range(warmup, total):
+        res = multi.step(prompts[k], pixels[k], grid, sync_timing=False)
+        toks += sum(min(len(r["new_tokens"]), NEW_TOKENS) for r in res)
+        n_fwd += multi.timing[-1]["n_forward"] - 1
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    out = {"streams": n_streams, "value": n_streams * rounds * FRAMES_PER_CHUNK / t, "unit": UNIT, "rounds": rounds, "warmup": warmup,
+           "ms_per_round": 1e3 * t / rounds, "decode_tok_s": toks / t, "kv_len": [e.cache.seq_len for e in multi.engines],
+           "gpu_launches": multi.total_launches() - l0, "batched_decode_steps": n_fwd,
+           "note": "per-stream eviction, ViT and prefill; ONE batched decode step per token for all streams (one weight sweep)"}
+    # the batched split-KV decode attention on its own: one launch pair per layer over all streams' caches
+    g, L = G7, G7.num_layers
+    caches = [e.cache for e in multi.engines]
+    slots = _abi.make_slots(caches, list(multi.kv_len.split(1)), list(multi.next_pos.split(1)), list(multi.kv_after.split(1)))
+    for b, c in enumerate(caches):
+        multi.kv_after[b] = c.seq_len
+    q = torch.randn(n_streams, g.num_heads, g.head_dim, device=dev).to(torch.bfloat16)
+    o = torch.empty_like(q)
+    n_tiles = max(c.seq_len for c in caches) // 128 + 1
+    splits = max(1, min(multi.max_splits, -(-n_tiles // 3)))
+
+    def att():
+        for li in range(L):
+            _abi.attn_decode_streams(caches[0].view, slots, li, q, o, g.num_heads, caches[0].capacity, multi.engines[0].scale, splits, multi.ws)
+    att()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        att()
+    ts = []
+    for _ in range(5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); gr.replay(); a1.record(); torch.cuda.synchronize()
+        ts.append(a0.elapsed_time(a1) * 1e-3 / L)
+    ta = statistics.median(ts)
+    byt = sum(c.seq_len for c in caches) * 2 * g.num_kv_heads * g.head_dim * 2
+    out["attn_decode_streams"] = {"bound": "hbm", "achieved": byt / ta / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byt / ta / 1e9 / pk["hbm_gbs"],
+                                  "us_per_launch": ta * 1e6, "splits": splits, "alg_bytes_per_launch": byt}
+    return out
+
+
 def run_gpu(args):
     from streaming_vlm_b200 import _abi, synthetic
     from streaming_vlm_b200.config import QWEN25VL_7B as G7
@@ -384,6 +458,15 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         else:
             line["cpu_baseline"] = None
+    if args.streams > 1:
+        ms = multi_stream_leg(engine, args.streams, max(2, args.steps // 2), 2, rank, dev, pk)
+        if dist is not None:
+            tt = torch.tensor([ms["value"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            ms["value_all_gpus"] = float(tt[0])
+        if rank == 0:
+            line["multi_stream"] = ms
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -397,6 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=8, help="streams per GPU of the extra multi-stream leg (BASELINE configs[3]); 1 = skip")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around timed region 1 (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,10 +30,11 @@ from .engine import IM_END, StreamingEngine
 
 
 class MultiStreamEngine:
-    def __init__(self, weights: dict, geo: Geometry, n_streams: int, capacity: int = 8192, device="cuda", **engine_kwargs):
+    def __init__(self, weights: dict, geo: Geometry, n_streams: int, capacity: int = 8192, device="cuda", share_weights_from=None,
+                 **engine_kwargs):
         if not 1 <= n_streams <= _abi.MAX_STREAMS:
             raise ValueError(f"1..{_abi.MAX_STREAMS} streams per engine, got {n_streams}")
-        first = StreamingEngine(weights, geo, capacity, device, **engine_kwargs)
+        first = StreamingEngine(weights, geo, capacity, device, share_weights_from=share_weights_from, **engine_kwargs)
         self.engines = [first] + [StreamingEngine(None, geo, capacity, device, share_weights_from=first, **engine_kwargs)
                                   for _ in range(n_streams - 1)]
         self.geo, self.device, self.n = geo, first.device, n_streams
@@ -52,8 +53,9 @@ class MultiStreamEngine:
         g = geo
         self._q_rot = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._o = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
-        # enough CTAs for two per SM, ~3 key tiles per CTA (see StreamingEngine.decode_step)
-        self.max_splits = max(1, min((capacity + 127) // 128, -(-592 // (g.num_kv_heads * B))))
+        # one wave of CTAs (splits x kv heads x streams <= 148 SMs) and >= ~3 key tiles per CTA: swept in
+        # benchmarks/streams_attn_sweep.py (B = 8: 4 splits, 22.9 us per layer for 95 MB = 0.63 of the HBM peak)
+        self.max_splits = max(1, min((capacity + 127) // 128, 148 // (g.num_kv_heads * B)))
         self.ws = torch.zeros(_abi.attn_workspace_bytes(B, g.num_heads, g.head_dim, self.max_splits) // 4 + 16, dtype=torch.float32,
                               device=dev)
         self._graphs, self._slots = {}, {}
