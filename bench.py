@@ -163,7 +163,8 @@ def workload_config():
     return {"workload": "configs[1]: Qwen2.5-VL-7B-architecture random-init, single stream per GPU, 2 fps 448x448 synthetic video, "
                         "steady state of the sink512/text-window512/vision-window16 policy (round 200, S~5.8k), per-second "
                         "commentary decode of 20 tokens, greedy",
-            "chunk": {"frames": FRAMES_PER_CHUNK, "vit_tokens": 1024, "llm_vision_tokens": 256, "new_tokens": NEW_TOKENS},
+            "chunk": {"frames": FRAMES_PER_CHUNK, "vit_tokens": 1024, "llm_vision_tokens": 256, "new_tokens": NEW_TOKENS,
+                      "input": "uint8 RGB frames [2,448,448,3]; normalise + patchify (svlm_frames_to_patches) inside the step"},
             "policy": {"window_size": 16, "text_round": 16, "text_sink": 512, "text_sliding_window": 512},
             "cache_flush": "inputs larger than L2 (15 GB of weights and a 0.33 GB KV working set are swept every step)"}
 
@@ -381,11 +382,13 @@ def run_gpu(args):
     engine.load_state(state, seed=rank)
     total = args.warmup + 2 * args.steps + 1
     base_i = engine.i
-    px_host = []
+    # on-wire format of a chunk: 2 RGB frames, uint8 [T, H, W, 3] (what a video decoder hands over); the ingest kernel
+    # (normalise + patchify, svlm_frames_to_patches) runs inside every timed step
+    fr_host = []
     for k in range(total):
-        p, grid = synthetic.patchify(synthetic.frames(base_i + k), G7, dtype=torch.float32)
-        px_host.append(p.pin_memory())
-    px_dev = [p.to(dev) for p in px_host[:args.warmup + args.steps]]
+        fr_host.append(synthetic.frames(base_i + k).permute(0, 2, 3, 1).contiguous().pin_memory())
+    fr_dev = [f.to(dev) for f in fr_host[:args.warmup + args.steps]]
+    grid = (1, fr_host[0].shape[1] // G7.patch_size, fr_host[0].shape[2] // G7.patch_size)
     prompts = [synthetic.round_prompt(base_i + k, seed=rank) for k in range(total)]
 
     def barrier():
@@ -397,8 +400,8 @@ def run_gpu(args):
         lat, toks = [], 0
         for k in range(k0, k0 + n):
             t0 = time.perf_counter()
-            px = px_host[k].to(dev, non_blocking=True) if host_pixels else px_dev[k]
-            r = engine.step(prompts[k], px, grid, sync_timing=False)
+            fr = fr_host[k].to(dev, non_blocking=True) if host_pixels else fr_dev[k]
+            r = engine.step(prompts[k], None, grid, sync_timing=False, frames=fr)
             torch.cuda.current_stream().synchronize()
             lat.append(time.perf_counter() - t0)
             toks += min(len(r["new_tokens"]), NEW_TOKENS)
@@ -420,7 +423,7 @@ def run_gpu(args):
             torch.cuda.profiler.stop()
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = engine.launches - launches0
-    # ---- timed region 2: end to end, pixel values from pinned host memory, token ids read back every step
+    # ---- timed region 2: end to end, uint8 frames from pinned host memory, token ids read back every step
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -435,7 +438,7 @@ def run_gpu(args):
 
     gen_s = sum(t["GEN"] for t in engine.timing[-args.steps:])
     n_ids = len(engine.prev_ids)
-    h2d = px_host[0].numel() * 4 + n_ids * 8
+    h2d = fr_host[0].numel() + n_ids * 8
     d2h = NEW_TOKENS * 8
     line = None
     if rank == 0:

@@ -223,6 +223,18 @@ int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slo
                              const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
                              size_t workspace_bytes, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (9) Frame ingest ("next" row f3).  Replaces the pixel half of `processor(text=..., videos=clip)`
+ * (inference/inference.py:390-395 -> HF Qwen2-VL video processor) for a clip that is already at its target size:
+ * uint8 RGB frames [T][H][W][3] (decord's on-wire layout) -> ViT patch rows [gt*gh*gw][3*Tp*P*P] in merge-unit-major
+ * order, normalised as (x - mean') / std' in fp32 with mean' = mean * 255, std' = std * 255 (HF's fused rescale +
+ * normalise); out is fp32 or bf16 (the ViT's patch embedding consumes bf16).  The bicubic resize of
+ * livecc_utils/video_process_patch.py:140-153 is NOT covered (sizes must be multiples of patch * merge).
+ * ------------------------------------------------------------------------------------- */
+int svlm_frames_to_patches(const void* frames_thwc_u8, int n_frames, int height, int width, int patch, int temporal_patch,
+                           int merge, const float* mean3_host, const float* std3_host, void* out, int out_is_bf16,
+                           void* stream);
+
 /* Scheduling aid of the decode loop (no reference counterpart: the reference leaves cache policy to the libraries it
  * calls): issues L2 prefetches for [ptr, ptr + bytes).  The session runner launches it on a side stream next to the
  * latency-bound decode attention so that the weights of the following projections are L2-resident when they start. */

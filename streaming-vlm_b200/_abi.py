@@ -24,6 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
+           "svlm_frames_to_patches",
            "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
@@ -96,6 +97,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
+    L.svlm_frames_to_patches.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), vp, c_int, vp]
     L.svlm_qkv_rope_append_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int,
                                                vp, vp, vp, c_int, i32p, vp]
     L.svlm_attn_decode_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_size_t,
@@ -266,6 +268,28 @@ def attn_decode_streams(geometry: "ArenaView", slots, layer, q, out, q_heads, ma
     ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     check(lib().svlm_attn_decode_streams(geometry.ref, slots, len(slots), layer, q.data_ptr(), out.data_ptr(), q_heads, max_kv_len,
                                          num_splits, ws_ptr, ws_bytes, scale, _stream()), "svlm_attn_decode_streams")
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def frames_to_patches(frames_thwc, out=None, patch=14, temporal_patch=2, merge=2, dtype=torch.bfloat16, mean=CLIP_MEAN, std=CLIP_STD):
+    """uint8 CUDA frames [T, H, W, 3] -> ViT patch rows [gt*gh*gw, 3*Tp*P*P] (fp32 or bf16) and the (gt, gh, gw) grid."""
+    _req_cuda(frames_thwc)
+    assert frames_thwc.dtype == torch.uint8 and frames_thwc.dim() == 4 and frames_thwc.shape[-1] == 3 and frames_thwc.is_contiguous()
+    t, h, w, _ = frames_thwc.shape
+    grid = (t // temporal_patch, h // patch, w // patch)
+    if out is None:
+        out = torch.empty(grid[0] * grid[1] * grid[2], 3 * temporal_patch * patch * patch, dtype=dtype, device=frames_thwc.device)
+    assert out.dtype in (torch.float32, torch.bfloat16) and out.is_contiguous()
+    # mean' = mean * 255, std' = std * 255 in fp32, the way HF fuses rescale and normalise
+    inv_rescale = 1.0 / (1.0 / 255.0)
+    m = (torch.tensor(mean, dtype=torch.float32) * inv_rescale).tolist()
+    s_ = (torch.tensor(std, dtype=torch.float32) * inv_rescale).tolist()
+    check(lib().svlm_frames_to_patches(frames_thwc.data_ptr(), t, h, w, patch, temporal_patch, merge, (c_float * 3)(*m), (c_float * 3)(*s_),
+                                       out.data_ptr(), 1 if out.dtype == torch.bfloat16 else 0, _stream()), "svlm_frames_to_patches")
+    return out, grid
 
 
 def prefetch_l2(t, nbytes=None):

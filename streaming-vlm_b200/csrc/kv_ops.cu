@@ -328,6 +328,40 @@ __global__ void __launch_bounds__(256) qkv_rope_append_streams_kernel(const Appe
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Frame ingest: uint8 RGB frames [T][H][W][3] (the decoder's layout) -> ViT patch rows [gt*gh*gw][3*Tp*P*P] in the
+// merge-unit-major order of the HF Qwen2-VL video processor, normalised with its fused arithmetic
+// (x - mean') / std' in fp32 (mean' = mean * 255, std' = std * 255; IEEE sub and div, no FMA / reciprocal).
+// One thread = two adjacent output elements (pw, pw + 1): one 4-byte (bf16) or 8-byte (fp32) store.
+// ---------------------------------------------------------------------------------------------------
+struct IngestParams {
+    int T, H, W, P, TP, M;
+    float mean[3], stdv[3];
+    int out_bf16;
+};
+
+__global__ void __launch_bounds__(256) frames_to_patches_kernel(const uint8_t* __restrict__ frames, void* __restrict__ out, const IngestParams p) {
+    const int gh = p.H / p.P, gw = p.W / p.P, gt = p.T / p.TP;
+    const int cols = 3 * p.TP * p.P * p.P;
+    const int64_t total2 = (int64_t)gt * gh * gw * cols / 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total2) return;
+    const int col = (int)((idx * 2) % cols);
+    int64_t n = (idx * 2) / cols;
+    const int pw = col % p.P, ph = (col / p.P) % p.P, ti = (col / (p.P * p.P)) % p.TP, c = col / (p.P * p.P * p.TP);
+    const int mw = (int)(n % p.M); n /= p.M;
+    const int mh = (int)(n % p.M); n /= p.M;
+    const int bw = (int)(n % (gw / p.M)); n /= (gw / p.M);
+    const int bh = (int)(n % (gh / p.M)); n /= (gh / p.M);
+    const int t = (int)n * p.TP + ti;
+    const int y = (bh * p.M + mh) * p.P + ph, x = (bw * p.M + mw) * p.P + pw;
+    const uint8_t* src = frames + (((int64_t)t * p.H + y) * p.W + x) * 3 + c;
+    const float v0 = __fdiv_rn(__fsub_rn((float)src[0], p.mean[c]), p.stdv[c]);
+    const float v1 = __fdiv_rn(__fsub_rn((float)src[3], p.mean[c]), p.stdv[c]);       // P is even: pw + 1 is in the same patch row
+    if (p.out_bf16) reinterpret_cast<uint32_t*>(out)[idx] = pack_bf16(v0, v1);
+    else reinterpret_cast<float2*>(out)[idx] = make_float2(v0, v1);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // vit_rope: qkv [N][3][H][D] bf16, q and k rotated in place.  fp32 products and sum, no FMA contraction
 // (apply_rotary_pos_emb_flashatt semantics: q.float()*cos + rotate_half(q.float())*sin, cast back).
 // One thread = one 8-element chunk of the first half and its partner chunk in the second half.
@@ -563,6 +597,25 @@ extern "C" int svlm_qkv_rope_append_streams(const svlm_arena_t* geometry, const 
                                                                                 (const uint16_t*)v, q_row_stride, k_row_stride,
                                                                                 v_row_stride, q_heads, (uint16_t*)q_out, tab);
     return launch_status("qkv_rope_append_streams_kernel");
+}
+
+extern "C" int svlm_frames_to_patches(const void* frames_thwc_u8, int n_frames, int height, int width, int patch, int temporal_patch,
+                                      int merge, const float* mean3_host, const float* std3_host, void* out, int out_is_bf16,
+                                      void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(frames_thwc_u8 && out && mean3_host && std3_host, "NULL argument");
+    SVLM_REQUIRE(patch > 0 && patch % 2 == 0 && temporal_patch > 0 && merge > 0, "bad patch / temporal_patch / merge");
+    SVLM_REQUIRE(n_frames > 0 && n_frames % temporal_patch == 0, "n_frames %d must be a positive multiple of temporal_patch %d", n_frames,
+                 temporal_patch);
+    SVLM_REQUIRE(height > 0 && width > 0 && height % (patch * merge) == 0 && width % (patch * merge) == 0,
+                 "frame size %dx%d must be a multiple of patch * merge = %d", height, width, patch * merge);
+    SVLM_REQUIRE(((uintptr_t)out & 7) == 0, "out must be 8-byte aligned");
+    IngestParams p{n_frames, height, width, patch, temporal_patch, merge, {mean3_host[0], mean3_host[1], mean3_host[2]},
+                   {std3_host[0], std3_host[1], std3_host[2]}, out_is_bf16 ? 1 : 0};
+    const int64_t total2 = (int64_t)n_frames * height * width * 3 / 2;
+    frames_to_patches_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames_thwc_u8, out, p);
+    return launch_status("frames_to_patches_kernel");
 }
 
 extern "C" int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int n_tokens, int heads, int head_dim, void* stream) {

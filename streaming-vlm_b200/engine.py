@@ -540,10 +540,21 @@ class StreamingEngine:
         self.i += 1
         return {"new_tokens": new_tokens, "input_len": input_len, "ids": seq, "runs": runs, "cache_len": self.cache.seq_len}
 
-    def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None):
+    def ingest(self, frames_thwc: torch.Tensor):
+        """uint8 RGB frames [T, H, W, 3] in HBM -> (bf16 patch rows for the ViT, grid): the pixel half of the reference's
+        `processor(text=..., videos=clip)` call (inference.py:390-395) for a clip already at its target size."""
+        g = self.geo
+        self.launches += 1
+        return _abi.frames_to_patches(frames_thwc, patch=g.patch_size, temporal_patch=g.temporal_patch_size, merge=g.spatial_merge_size)
+
+    def step(self, prompt_ids, pixels, grid, previous_text="", taps=None, sync_timing=True, forced=None, frames=None):
+        """One chunk.  Either `pixels` (patch rows as the HF processor would emit them) or `frames` (uint8 [T, H, W, 3] on
+        the device, run through `ingest`) carries the video; `grid` is ignored when `frames` is given."""
         if sync_timing:
             torch.cuda.synchronize()
         self._mark("step_start")
+        if frames is not None:
+            pixels, grid = self.ingest(frames)
         t0 = time.perf_counter()
         ids, runs = self.begin_step(prompt_ids, grid, previous_text)
         if sync_timing:

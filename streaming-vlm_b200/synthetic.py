@@ -71,15 +71,18 @@ def frames(i: int, height: int = 448, width: int = 448, n: int = 2, seed: int = 
 def patchify(fr: torch.Tensor, geo: Geometry, dtype=torch.float32):
     """uint8 [T, 3, H, W] -> (pixel_values [gt*gh*gw, C*Tp*P*P], grid (gt, gh, gw)).
 
-    Same arithmetic and ordering as the HF Qwen2-VL image processor: rescale 1/255,
+    Same arithmetic and ordering as the HF Qwen2-VL video processor: fused rescale 1/255 +
     CLIP mean/std, then (gt, Tp, C, gh/m, m, P, gw/m, m, P) -> (gt, gh/m, gw/m, m, m, C, Tp, P, P).
     """
     t, c, h, w = fr.shape
     p, tp, m = geo.patch_size, geo.temporal_patch_size, geo.spatial_merge_size
     gt, gh, gw = t // tp, h // p, w // p
-    mean = torch.tensor(CLIP_MEAN, device=fr.device).view(1, 3, 1, 1)
-    std = torch.tensor(CLIP_STD, device=fr.device).view(1, 3, 1, 1)
-    x = (fr.to(torch.float32) * (1.0 / 255.0) - mean) / std
+    # fused rescale + normalise exactly as HF's fast processor does it (bit-exact against Qwen2VLVideoProcessor 5.5.0,
+    # tests/golden/frame_ingest.npz): mean' = mean * 255, std' = std * 255 in fp32, then (x - mean') / std'
+    inv_rescale = 1.0 / (1.0 / 255.0)
+    mean = (torch.tensor(CLIP_MEAN) * inv_rescale).to(fr.device).view(1, 3, 1, 1)
+    std = (torch.tensor(CLIP_STD) * inv_rescale).to(fr.device).view(1, 3, 1, 1)
+    x = (fr.to(torch.float32) - mean) / std
     x = x.reshape(gt, tp, c, gh // m, m, p, gw // m, m, p).permute(0, 3, 6, 4, 7, 2, 1, 5, 8)
     return x.reshape(gt * gh * gw, c * tp * p * p).to(dtype).contiguous(), (gt, gh, gw)
 

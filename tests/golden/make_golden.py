@@ -16,6 +16,7 @@ stored.
                                       (qwen_vl_utils.vision_process.FPS of the pinned 0.0.11)
     apply_multimodal_rotary_pos_emb   exec'd from qwen2_5/language_forward.py with HF's
                                       `rotate_half` (same function in 4.52 and 5.5)
+    Qwen2VLVideoProcessor             HF 5.5.0, the processor class behind the reference's `processor(videos=...)`
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -248,6 +249,28 @@ def main():
                         cos=cos.view(torch.int16).numpy(), sin=sin.view(torch.int16).numpy(),
                         q_rot=qe.view(torch.int16).numpy(), k_rot=ke.view(torch.int16).numpy())
     print("mrope", qe.shape, ke.shape)
+    make_frame_ingest()
+
+
+def make_frame_ingest():
+    """Frame ingest: the HF processor the reference calls (`processor(text=..., videos=clip)`, inference.py:390-395) run on
+    seeded uint8 frames that are already at their target size.  transformers 5.5.0 is the only version in the image (the
+    reference pins 4.52.4, use_fast=False); stored: the full fp32 output for a 112 x 112 clip and a SHA-256 for 448 x 448."""
+    from transformers import Qwen2VLVideoProcessor
+    vp = Qwen2VLVideoProcessor(min_pixels=4 * 28 * 28, max_pixels=16384 * 28 * 28)
+    out = {}
+    for name, (h, w, seed) in {"small": (112, 112, 3), "wide": (56, 168, 4)}.items():
+        fr = synthetic.frames(seed, h, w)                                  # uint8 [2, 3, H, W]
+        r = vp(videos=[fr], return_tensors="pt", do_resize=False)
+        out[name + "__frames_thwc"] = fr.permute(0, 2, 3, 1).contiguous().numpy()
+        out[name + "__pixel_values"] = r["pixel_values_videos"].numpy()
+        out[name + "__grid"] = r["video_grid_thw"].numpy()
+    fr = synthetic.frames(5, 448, 448)
+    r = vp(videos=[fr], return_tensors="pt", do_resize=False)
+    out["full__sha256"] = np.frombuffer(hashlib.sha256(r["pixel_values_videos"].numpy().tobytes()).digest(), dtype=np.uint8)
+    out["full__seed_hw"] = np.array([5, 448, 448])
+    np.savez_compressed(os.path.join(HERE, "frame_ingest.npz"), **out)
+    print("frame ingest", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

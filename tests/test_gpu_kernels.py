@@ -502,3 +502,29 @@ def test_streams_argument_errors(abi):
         abi.attn_decode_streams(view, slots, 0, q[:1], q[:1].clone(), 4, 256, 0.1, 4, None)
     with pytest.raises(RuntimeError, match="layer"):
         abi.attn_decode_streams(view, slots, 5, q[:1], q[:1].clone(), 4, 256, 0.1, 1, None)
+
+
+# ------------------------------------------------------------------------------------------------ frame ingest (row f3)
+@pytest.mark.gpu
+def test_frames_to_patches_bit_exact(abi, golden_dir):
+    from oracle import frames as o_frames
+    from streaming_vlm_b200 import synthetic
+    z = np.load(os.path.join(golden_dir, "frame_ingest.npz"))
+    cases = [torch.from_numpy(z[n + "__frames_thwc"]) for n in ("small", "wide")]
+    cases.append(synthetic.frames(5, 448, 448).permute(0, 2, 3, 1).contiguous())
+    cases.append(synthetic.frames(6, 56, 56, n=6).permute(0, 2, 3, 1).contiguous())            # three temporal patches
+    for fr in cases:
+        want, grid = o_frames.frames_to_patches(fr)
+        got32, g32 = abi.frames_to_patches(fr.to(DEV), dtype=torch.float32)
+        got16, g16 = abi.frames_to_patches(fr.to(DEV), dtype=torch.bfloat16)
+        torch.cuda.synchronize()
+        assert g32 == grid and g16 == grid
+        assert torch.equal(got32.cpu().view(torch.int32), want.view(torch.int32))
+        assert torch.equal(bits(got16.cpu()), bits(want.to(torch.bfloat16)))
+    # and against the HF processor's own output
+    got, _ = abi.frames_to_patches(cases[0].to(DEV), dtype=torch.float32)
+    assert np.array_equal(got.cpu().numpy().view(np.int32), z["small__pixel_values"].view(np.int32))
+    with pytest.raises(RuntimeError, match="multiple of patch"):
+        abi.frames_to_patches(torch.zeros(2, 30, 56, 3, dtype=torch.uint8, device=DEV))
+    with pytest.raises(RuntimeError, match="temporal_patch"):
+        abi.frames_to_patches(torch.zeros(3, 56, 56, 3, dtype=torch.uint8, device=DEV))

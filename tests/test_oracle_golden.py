@@ -109,3 +109,26 @@ def test_rotary_table_equals_per_position_embedding(golden_dir):
         idx = pos[ax, 0].long()
         _bf16_close(tc[idx], cos[ax, 0, :, :64], "cos table")
         _bf16_close(ts[idx], sin[ax, 0, :, 64:], "sin table")
+
+
+# ------------------------------------------------------------------------------------------------ frame ingest (row f3)
+def test_frame_ingest_oracle_equals_hf_processor(golden_dir):
+    """oracle/frames.py == the HF Qwen2-VL video processor's own output (fixture), bit for bit in fp32."""
+    import hashlib
+    from oracle import frames as o_frames
+    from streaming_vlm_b200 import synthetic
+    from streaming_vlm_b200.config import QWEN25VL_7B
+    z = np.load(os.path.join(golden_dir, "frame_ingest.npz"))
+    for name in ("small", "wide"):
+        fr = torch.from_numpy(z[name + "__frames_thwc"])
+        got, grid = o_frames.frames_to_patches(fr)
+        assert list(grid) == z[name + "__grid"][0].tolist()
+        assert np.array_equal(got.numpy().view(np.int32), z[name + "__pixel_values"].view(np.int32)), name
+        # the synthetic-data helper used by the benches and session tests is the same arithmetic
+        mine, grid2 = synthetic.patchify(fr.permute(0, 3, 1, 2).contiguous(), QWEN25VL_7B)
+        assert grid2 == grid and torch.equal(mine, got)
+    seed, h, w = (int(x) for x in z["full__seed_hw"])
+    fr = synthetic.frames(seed, h, w).permute(0, 2, 3, 1).contiguous()
+    got, grid = o_frames.frames_to_patches(fr)
+    assert grid == (1, 32, 32) and got.shape == (1024, 1176)
+    assert hashlib.sha256(got.numpy().tobytes()).digest() == bytes(z["full__sha256"])
