@@ -35,7 +35,7 @@ from .tokens import IM_END, LF, VIDEO_PAD
 from .vit import rmsnorm, vision_forward
 
 
-def llm_layer(x, w, li, geo, cache, cos, sin, taps=None):
+def llm_layer(x, w, li, geo, cache, cos, sin, taps=None, pos_mode="shrink"):
     p = f"model.language_model.layers.{li}."
     t = x.shape[0]
     hq, hkv, d = geo["num_heads"], geo["num_kv_heads"], geo["head_dim"]
@@ -46,8 +46,14 @@ def llm_layer(x, w, li, geo, cache, cos, sin, taps=None):
     q = q.view(1, t, hq, d).transpose(1, 2)
     k = k.view(1, t, hkv, d).transpose(1, 2)
     v = v.view(1, t, hkv, d).transpose(1, 2)
-    k_all, v_all = cache.update(k, v, li)                  # raw keys are cached
-    q_rot, k_rot = apply_mrope(q, k_all, cos, sin, geo["mrope_section"])
+    if pos_mode == "append":
+        # append mode (language_forward.py:184-188): cos/sin cover the NEW tokens only; the ROTATED keys are cached and
+        # never touched again
+        q_rot, k_new = apply_mrope(q, k, cos, sin, geo["mrope_section"])
+        k_rot, v_all = cache.update(k_new, v, li)
+    else:
+        k_all, v_all = cache.update(k, v, li)                  # raw keys are cached
+        q_rot, k_rot = apply_mrope(q, k_all, cos, sin, geo["mrope_section"])
     o = attention(q_rot[0], k_rot[0], v_all[0], causal=True)
     if taps is not None:
         taps.setdefault("attn_out", []).append(o)
@@ -60,8 +66,11 @@ def llm_layer(x, w, li, geo, cache, cos, sin, taps=None):
     return x + F.linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"])
 
 
-def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_grid=None, taps=None, timers=None):
-    """One forward over the uncached ids.  Returns fp32 logits of the last position."""
+def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_grid=None, taps=None, timers=None,
+                  pos_mode="shrink", state=None):
+    """One forward over the uncached ids.  Returns fp32 logits of the last position.
+    `pos_mode="append"` (model_forward.py:112-153): positions of the new tokens only, continuing after
+    `state["last_cache_position"]`; the grids of THIS call (`pixel_grid`) feed `get_rope_index`."""
     ids_t = torch.tensor(new_ids, dtype=torch.long)
     x = F.embedding(ids_t, w["model.language_model.embed_tokens.weight"])
     if pixels is not None:
@@ -76,14 +85,24 @@ def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_gr
         x[mask] = vid.to(x.dtype)
         if taps is not None:
             taps["video_embeds"] = vid
-    pos, _ = get_rope_index(full_ids, grids, geo["spatial_merge_size"], geo["tokens_per_second"])
-    cache.update_position_ids(pos)
+    if pos_mode == "append":
+        if cache.get_seq_length() == 0:                                            # prefill (:114-127)
+            pos, _ = get_rope_index(new_ids, pixel_grid, geo["spatial_merge_size"], geo["tokens_per_second"])
+        elif len(new_ids) != 1:                                                    # chunk prefill (:128-137)
+            pos, _ = get_rope_index(new_ids, pixel_grid, geo["spatial_merge_size"], geo["tokens_per_second"])
+            pos = pos + float(state["last_cache_position"] + 1)
+        else:                                                                      # decode (:138-151)
+            pos = torch.full((3, 1, 1), float(state["last_cache_position"] + 1))
+        state["last_cache_position"] = int(pos[0, 0, -1])                          # (:153)
+    else:
+        pos, _ = get_rope_index(full_ids, grids, geo["spatial_merge_size"], geo["tokens_per_second"])
+        cache.update_position_ids(pos)
     cos, sin = rotary_cos_sin(pos, default_inv_freq(geo["head_dim"], geo["rope_theta"]), x.dtype)
     if taps is not None:
         taps["position_ids"] = pos
     t0 = time.perf_counter()
     for li in range(geo["num_layers"]):
-        x = llm_layer(x, w, li, geo, cache, cos, sin, taps)
+        x = llm_layer(x, w, li, geo, cache, cos, sin, taps, pos_mode)
     if timers is not None:
         key = "prefill_layers" if len(new_ids) > 1 else "decode_layers"
         timers[key] = timers.get(key, 0.0) + time.perf_counter() - t0
@@ -100,7 +119,10 @@ class Session:
     the caller as token-id lists (no tokenizer exists offline)."""
 
     def __init__(self, w, geo, window_size=16, text_round=16, text_sink=512, text_sliding_window=512,
-                 max_new_tokens=20, suppress=None, assistant_start_bias=3, assistant_end_bias=2):
+                 max_new_tokens=20, suppress=None, assistant_start_bias=3, assistant_end_bias=2, pos_mode="shrink"):
+        assert pos_mode in ("append", "shrink"), "pos_mode must be in ['append', 'shrink']"      # streaming_args.py:5
+        self.pos_mode = pos_mode
+        self.pos_state = {"last_cache_position": -1}
         self.w, self.geo = w, geo
         self.window_size, self.text_round = window_size, text_round
         self.text_sink, self.text_sliding_window = text_sink, text_sliding_window
@@ -154,7 +176,7 @@ class Session:
             new = seq[cached:]
             px = pixels if n_fwd == 0 else None
             logits = model_forward(new, full, self.grids, self.cache, self.w, self.geo, px, [tuple(grid)],
-                                   taps if n_fwd == 0 else None, timers)
+                                   taps if n_fwd == 0 else None, timers, self.pos_mode, self.pos_state)
             full = full + [0]                   # F.pad(ids, (0,1)) after every forward
             n_fwd += 1
             if self.suppress is not None:

@@ -91,7 +91,8 @@ class StreamingEngine:
     def __init__(self, weights: dict, geo: Geometry, capacity: int = 8192, device="cuda", window_size=DEFAULT_WINDOW_SIZE,
                  text_round=DEFAULT_TEXT_ROUND, text_sink=DEFAULT_TEXT_SINK, text_sliding_window=DEFAULT_TEXT_SLIDING_WINDOW,
                  max_new_tokens=MAX_TOKEN_PER_DURATION, suppress=None, assistant_start_bias=3, assistant_end_bias=2,
-                 use_graph=True, decode_splits=None, prefill_splits=None, share_weights_from=None):
+                 use_graph=True, decode_splits=None, prefill_splits=None, share_weights_from=None, pos_mode="shrink",
+                 max_position=None):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         _abi.lib()
@@ -102,7 +103,16 @@ class StreamingEngine:
         self.asb, self.aeb = assistant_start_bias, assistant_end_bias
         self.use_graph = use_graph
         self.suppress = None if suppress is None else suppress.to(self.device)
-        self.cache = StreamingCache(geo, capacity, self.device)
+        # StreamingArgs.pos_mode (streaming_args.py:1-10): "shrink" re-indexes the retained tokens contiguously after every
+        # eviction (the reference's default); "append" keeps every token's position for ever ("grows indefinitely"), so the
+        # rotary tables must cover the whole stream: `max_position` rows (default 131072 = ~40 min of 448x448 video at 2 fps)
+        if pos_mode not in ("append", "shrink"):
+            raise ValueError("pos_mode must be in ['append', 'shrink']")
+        self.pos_mode = pos_mode
+        if pos_mode == "append" and max_position is None:
+            max_position = 1 << 17
+        self.cache = StreamingCache(geo, capacity, self.device, max_position=max_position)
+        self._pos_upper = 0          # host-side upper bound of the largest position handed out (append mode)
         self.scale = 1.0 / math.sqrt(geo.head_dim)
         self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 296 // geo.num_kv_heads))   # two CTAs per SM
         self.prefill_splits = prefill_splits
@@ -521,9 +531,23 @@ class StreamingEngine:
         if getattr(self, "_grids_uploaded", None) != want:
             c.set_video_grids(want)
             self._grids_uploaded = list(want)
+        moved = runs is not None and not (len(runs) == 1 and runs[0] == (0, 0, c.seq_len))
+        if self.pos_mode == "append":
+            if moved:
+                c.gather_positions(runs)
+                c.compact(runs)
+                self.launches += 1
+            self._pos_upper += len(ids) - c.seq_len + self.max_new_tokens
+            if self._pos_upper >= c.cos_table.shape[0]:
+                raise RuntimeError(f"append-mode positions would exceed the rotary table ({c.cos_table.shape[0]} rows): "
+                                   "construct the engine with a larger max_position")
+            c.append_positions(ids, c.seq_len, self.grids[-1])
+            self._grids_uploaded = None
+            self.launches += 1
+            return ids, runs
         c.compute_positions(ids)
         self.launches += 1
-        if runs is not None and not (len(runs) == 1 and runs[0] == (0, 0, c.seq_len)):
+        if moved:
             c.compact(runs)
             self.launches += 1
         return ids, runs
@@ -531,6 +555,13 @@ class StreamingEngine:
     def finish_step(self, ids, seq, runs, t_pkv=0.0, t_gen=0.0, n_fwd=0):
         """Bookkeeping after generation (inference.py:457-517): close the turn, remember the ids, extend the history."""
         input_len = len(ids)
+        if self.pos_mode == "append":
+            # the decode kernels rotate at `next_pos` without recording it; append mode needs the position of every cached row
+            # again at the next compaction: rows input_len .. seq_len-1 hold consecutive text positions ending at next_pos - 1
+            c = self.cache
+            n_dec = c.seq_len - input_len
+            if n_dec > 0:
+                c.pos[:, input_len:c.seq_len] = (c.next_pos - n_dec) + torch.arange(n_dec, dtype=torch.int32, device=self.device)
         if seq[-1] != IM_END:
             seq.append(IM_END)
         new_tokens = seq[input_len:]

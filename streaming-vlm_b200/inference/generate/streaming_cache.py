@@ -176,6 +176,30 @@ class StreamingCache:
                              self.spatial_merge, self.t_step, TOKEN_IDS["<|video_pad|>"])
         return n
 
+    # -- append position mode (reference: model_forward.py:112-153 + language_forward.py:184-188) -----------------
+    def gather_positions(self, runs):
+        """Retained tokens KEEP their positions in append mode: move them with the same runs as the K/V rows, so that the
+        compaction kernel re-derives exactly the K_rot the token was appended with."""
+        n = sum(r[2] for r in runs)
+        self.pos[:, :n] = torch.cat([self.pos[:, s_:s_ + l] for s_, _, l in runs], dim=1)
+
+    def append_positions(self, ids, start: int, grid) -> int:
+        """Positions of the uncached ids `ids[start:]` only: `get_rope_index` over the new ids with THIS chunk's grid, shifted by
+        last_cache_position + 1 (= `next_pos`, which the decode steps keep advancing); nothing is recomputed for the cache."""
+        n = self.upload_ids(ids)
+        n_new = n - start
+        offset = self.next_pos.clone()
+        if start == 0:
+            offset.zero_()
+        self.set_video_grids([grid])
+        if not hasattr(self, "_pos_rel"):
+            self._pos_rel = torch.zeros_like(self.pos)
+        _abi.mrope_positions(self.ids_dev[start:], n_new, self.grids, self.n_grids, self._pos_rel, self.next_pos, self.status,
+                             self.spatial_merge, self.t_step, TOKEN_IDS["<|video_pad|>"])
+        self.pos[:, start:n] = self._pos_rel[:, :n_new] + offset
+        self.next_pos += offset
+        return n
+
     def compact(self, runs, new_ids=None):
         """Gather `runs` = [(src, dst, len)] from the live buffer into the other one, re-rotating K at the
         positions of `new_ids` (the pruned sequence; omitted = positions already in `self.pos`)."""

@@ -24,14 +24,14 @@ LOGIT_TOL = 0.08        # |logit| ~ 1; bf16 hidden state (8 mantissa bits) throu
 ATTN_TOL = dict(rtol=3e-2, atol=2e-2)
 
 
-def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, check_every=1):
+def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, check_every=1, pos_mode="shrink"):
     from streaming_vlm_b200.engine import StreamingEngine
     geo = TINY
     w_cpu = synthetic.random_weights(geo, seed=0)
     suppress = synthetic.suppress_mask(geo.vocab)
-    oracle = Session(w_cpu, geo.as_dict(), window, text_round, sink, sliding, suppress=suppress)
+    oracle = Session(w_cpu, geo.as_dict(), window, text_round, sink, sliding, suppress=suppress, pos_mode=pos_mode)
     engine = StreamingEngine({k: v.clone() for k, v in w_cpu.items()}, geo, capacity=8192, window_size=window,
-                             text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress)
+                             text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress, pos_mode=pos_mode)
     n_vis = (height // 28) * (width // 28)
     mismatches, total, prev_cache_len = 0, 0, 0
     for i in range(n_chunks):
@@ -52,14 +52,20 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
         if deep:
             n = rg["input_len"]
             pos_ref = taps_o["position_ids"][:, 0, :].numpy()
-            # engine positions cover ids of the prefill; decode tokens continue the text run
             pos_got = engine.cache.pos[:, :n].cpu().numpy().astype(np.float32)
-            assert np.array_equal(pos_got, pos_ref[:, :n]), f"chunk {i}: positions"
-            # K_rot == reference mRoPE applied to the arena's own K_raw at those positions (bit-exact)
+            if pos_mode == "append":
+                # the oracle (like the reference) only ever computes the positions of the NEW tokens; retained tokens keep theirs
+                t_new = pos_ref.shape[1]
+                assert np.array_equal(pos_got[:, n - t_new:n], pos_ref), f"chunk {i}: positions of the new tokens"
+                idx = engine.cache.pos[:, :n].cpu().long()
+            else:
+                # engine positions cover ids of the prefill; decode tokens continue the text run
+                assert np.array_equal(pos_got, pos_ref[:, :n]), f"chunk {i}: positions"
+                idx = taps_o["position_ids"][:, 0, :n].long()
+            # K_rot == reference mRoPE applied to the arena's own K_raw at those positions (bit-exact); cos/sin gathered from
+            # the engine's own host-built table (same arithmetic as HF's rotary module, see
+            # tests/test_oracle_golden.py::test_rotary_table_equals_per_position_embedding)
             k_raw, k_rot, _ = engine.cache.planes(0)
-            # cos/sin gathered from the engine's own host-built table (same arithmetic as HF's rotary module, see
-            # tests/test_oracle_golden.py::test_rotary_table_equals_per_position_embedding) at the ORACLE's positions
-            idx = taps_o["position_ids"][:, 0, :n].long()
             tc, ts = engine.cache.cos_table.cpu()[idx], engine.cache.sin_table.cpu()[idx]
             cos, sin = torch.cat((tc, tc), dim=-1)[:, None], torch.cat((ts, ts), dim=-1)[:, None]
             kr = k_raw[:, :n].cpu()
@@ -94,4 +100,14 @@ def test_tiny_stream_config1():
     """BASELINE.json configs[0]: 64 frames of 448x448 = 32 chunks, defaults 16/16/512/512."""
     mism, total, engine, oracle = _run(32, 448, 448, 16, 16, 512, 512, 24, check_every=4)
     assert engine.cache.compactions >= 15
+    assert mism <= max(2, total // 20), (mism, total)
+
+
+def test_tiny_stream_append_position_mode():
+    """`pos_mode="append"` (StreamingArgs, model_forward.py:112-153): positions keep growing while the cache is pruned; retained
+    keys keep the rotation they were appended with.  Same checks as the shrink-mode stream, every eviction branch included."""
+    mism, total, engine, oracle = _run(20, 112, 112, 4, 4, 16, 24, 6, pos_mode="append")
+    assert engine.cache.compactions >= 14
+    assert int(engine.cache.next_pos) == oracle.pos_state["last_cache_position"] + 1
+    assert int(engine.cache.next_pos) > 2 * engine.cache.seq_len          # positions really outgrew the cache
     assert mism <= max(2, total // 20), (mism, total)
