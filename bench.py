@@ -462,7 +462,11 @@ def run_gpu(args):
         else:
             line["cpu_baseline"] = None
     if args.streams > 1:
-        ms = multi_stream_leg(engine, args.streams, max(2, args.steps // 2), 2, rank, dev, pk)
+        # extra leg: it must never cost the headline line (every rank still takes part in the all-reduce below)
+        try:
+            ms = multi_stream_leg(engine, args.streams, max(2, args.steps // 2), 2, rank, dev, pk)
+        except Exception as exc:   # noqa: BLE001
+            ms = {"streams": args.streams, "value": 0.0, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
         if dist is not None:
             tt = torch.tensor([ms["value"]], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.SUM)
