@@ -286,7 +286,7 @@ def kernel_rooflines(engine, pk):
 def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     """BASELINE configs[3] at this GPU: `n_streams` independent 7B streams sharing the GPU (and one copy of the weights), each
     in the same steady state as the headline stream but with its own frames, prompts and cache contents.  One ROUND = one
-    chunk of every stream (per-stream eviction, ViT and prefill, then batched decode steps).  Pixel values resident in HBM."""
+    chunk of every stream (per-stream eviction, batched ViT + chunk prefill, then batched decode steps).  Pixel values resident in HBM."""
     from streaming_vlm_b200 import _abi, synthetic
     from streaming_vlm_b200.config import QWEN25VL_7B as G7
     from streaming_vlm_b200.multi_stream import MultiStreamEngine
@@ -325,7 +325,7 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     out = {"streams": n_streams, "value": n_streams * rounds * FRAMES_PER_CHUNK / t, "unit": UNIT, "rounds": rounds, "warmup": warmup,
            "ms_per_round": 1e3 * t / rounds, "decode_tok_s": toks / t, "kv_len": [e.cache.seq_len for e in multi.engines],
            "gpu_launches": multi.total_launches() - l0, "batched_decode_steps": n_fwd,
-           "note": "per-stream eviction, ViT and prefill; ONE batched decode step per token for all streams (one weight sweep)"}
+           "note": "per-stream eviction; ViT and chunk prefill of all streams in one pass; ONE batched decode step per token for all streams (one weight sweep each)"}
     # the batched split-KV decode attention on its own: one launch pair per layer over all streams' caches
     g, L = G7, G7.num_layers
     caches = [e.cache for e in multi.engines]

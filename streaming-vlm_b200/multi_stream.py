@@ -59,6 +59,9 @@ class MultiStreamEngine:
         self.ws = torch.zeros(_abi.attn_workspace_bytes(B, g.num_heads, g.head_dim, self.max_splits) // 4 + 16, dtype=torch.float32,
                               device=dev)
         self._graphs, self._slots = {}, {}
+        self._pf_graphs = {}
+        self._pf_ids = torch.zeros(B * 1024, dtype=torch.int64, device=dev)
+        self.batch_prefill = True      # ViT and chunk prefill of all streams in one pass (one weight sweep); False = per stream
         self.use_graph = first.use_graph
         self.launches = 0
         self.timing = []
@@ -123,6 +126,98 @@ class MultiStreamEngine:
         entry[0].replay()
         self.launches += entry[1]
 
+    # ------------------------------------------------------------------ batched ViT + chunk prefill
+    def _prefill_body(self, ids, metas, video, last):
+        """Chunk prefill of all streams in ONE pass over the weights: the dense projections see the concatenated new tokens of
+        every stream; append and attention run per stream on its own arena (rows / lengths from device memory).
+        metas[b] = (row offset, T_b, video-token runs, splits); video = [sum(video tokens), hidden] in stream order."""
+        e0, g = self.engines[0], self.geo
+        hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
+        total = ids.numel()
+        before = e0.launches
+        x = F.embedding(ids, e0.embed)
+        vo = 0
+        for off, t, runs, _ in metas:
+            for a, n in runs:
+                x[off + a:off + a + n] = video[vo:vo + n]
+                vo += n
+        pending = None
+        for li, L in enumerate(e0.layers):
+            x, h = e0._add_norm(x, pending, L["ln1"], g.rms_eps)
+            qkv = F.linear(h, L["wqkv"], L["bqkv"])
+            q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
+            q_rot = torch.empty(total, hq, d, dtype=torch.bfloat16, device=self.device)
+            o = torch.empty(total, hq, d, dtype=torch.bfloat16, device=self.device)
+            for e, (off, t, _, splits) in zip(self.engines, metas):
+                c, sl = e.cache, slice(off, off + t)
+                _abi.qkv_rope_append(c.view, c.cur, li, q[sl], k[sl], v[sl], t, hq, q_rot[sl], 0, c.pos, c.cos_table, c.sin_table, c.section,
+                                     start_dev=e.kv_len_dev)
+                _abi.attn_causal(c.view, c.cur, li, q_rot[sl], o[sl], t, hq, c.capacity, e.scale, splits, e.ws if splits > 1 else None,
+                                 kv_len_dev=e.kv_after_dev)
+                self.launches += 2 + (1 if splits > 1 else 0)
+            x, h = e0._add_norm(x, F.linear(o.view(total, -1), L["wo"]), L["ln2"], g.rms_eps)
+            pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
+        logits = e0._logits(x[last], pending[last])           # `last`: row of the last new token of every stream
+        self.tok.copy_(torch.argmax(logits, dim=-1))
+        self.launches += e0.launches - before
+        e0.launches = before
+
+    def _vit_and_prefill_all(self, ids_all, pixels, grid):
+        """Batched ViT (the chunks of all streams are the temporal slices of one (B*t, h, w) grid: windows and full attention
+        are per slice, so this is exactly B independent towers) followed by the batched chunk prefill."""
+        import numpy as np
+        from .engine import VIDEO_PAD
+        engines, g = self.engines, self.geo
+        e0 = engines[0]
+        video = e0.vision_forward(torch.cat(pixels, dim=0), (grid[0] * self.n, grid[1], grid[2]))
+        metas, off, pos = [], 0, 0
+        for e, ids in zip(engines, ids_all):
+            c = e.cache
+            new_ids = np.asarray(ids[c.seq_len:])
+            t, start = len(new_ids), c.seq_len
+            if start + t > c.capacity:
+                raise RuntimeError(f"sequence of {start + t} tokens exceeds the arena capacity {c.capacity}")
+            where = np.flatnonzero(new_ids == VIDEO_PAD)
+            brk = np.flatnonzero(np.diff(where) != 1) + 1
+            runs = tuple((int(where[a]), int(b - a)) for a, b in zip(np.concatenate([[0], brk]), np.concatenate([brk, [where.size]]))) if where.size else ()
+            splits = e.prefill_splits or (1 if (-(-t // (128 // g.group))) * g.num_kv_heads >= 74 or start + t < 2048 or t > 512 else 2)
+            metas.append((off, t, runs, splits))
+            self._pf_ids[off:off + t].copy_(c.ids_dev[start:start + t])
+            e.kv_len_dev.fill_(start)
+            e.kv_after_dev.fill_(start + t)
+            off += t
+            pos += int(where.size)
+        if pos != video.shape[0]:
+            raise ValueError(f"Video features and video tokens do not match: tokens: {pos}, features {video.shape[0]}")
+        ids = self._pf_ids[:off]
+        key = (tuple(metas), tuple(e.cache.cur for e in engines), video.data_ptr())
+        entry = self._pf_graphs.get(key) if self.use_graph else None
+        if entry is None:
+            last = torch.tensor([o_ + t - 1 for o_, t, _, _ in metas], dtype=torch.long, device=self.device)
+            if not self.use_graph:
+                self._prefill_body(ids, metas, video, last)
+            else:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._prefill_body(ids, metas, video, last)            # warm-up outside capture (appends the same rows again)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                before = self.launches
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._prefill_body(ids, metas, video, last)
+                entry = self._pf_graphs[key] = (gr, self.launches - before, last)
+                self.launches = before
+        if entry is not None:
+            entry[0].replay()
+            self.launches += entry[1]
+        for e, (_, t, _, _) in zip(engines, metas):
+            e.cache.seq_len += t
+            e.cache._seen_tokens += t
+            e.kv_len_dev.fill_(e.cache.seq_len)
+            e.kv_after_dev.fill_(e.cache.seq_len + 1)
+
     # ------------------------------------------------------------------ one chunk of every stream
     def step(self, prompts, pixels, grid, previous_text="", forced=None, sync_timing=True):
         """One chunk for each stream (`prompts[b]`, `pixels[b]`; same grid).  `forced[b]`: teacher-forced tokens of stream b
@@ -140,13 +235,19 @@ class MultiStreamEngine:
             torch.cuda.synchronize()
         t_pkv = time.perf_counter() - t0
         t0 = time.perf_counter()
-        for b, e in enumerate(engines):
-            c = e.cache
-            video = e.vision_forward(pixels[b], grid) if pixels[b] is not None else None
-            logits = e.prefill(ids_all[b][c.seq_len:], video)
-            e.tok_dev.copy_(torch.argmax(logits, dim=-1))
-            e.kv_len_dev.fill_(c.seq_len)
-            e.kv_after_dev.fill_(c.seq_len + 1)
+        batched = (self.batch_prefill and all(p is not None for p in pixels) and len({tuple(p.shape) for p in pixels}) == 1
+                   and all(len(ids_all[b]) - e.cache.seq_len >= 2 for b, e in enumerate(engines))
+                   and sum(len(ids_all[b]) - e.cache.seq_len for b, e in enumerate(engines)) <= self._pf_ids.numel())
+        if batched:
+            self._vit_and_prefill_all(ids_all, pixels, grid)
+        else:
+            for b, e in enumerate(engines):
+                c = e.cache
+                video = e.vision_forward(pixels[b], grid) if pixels[b] is not None else None
+                logits = e.prefill(ids_all[b][c.seq_len:], video)
+                e.tok_dev.copy_(torch.argmax(logits, dim=-1))
+                e.kv_len_dev.fill_(c.seq_len)
+                e.kv_after_dev.fill_(c.seq_len + 1)
         seqs = [list(ids) for ids in ids_all]
         done = [False] * B
         argmaxes = [[] for _ in range(B)]

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 LOGIT_TOL = 0.08
 
 
-def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, use_graph=True):
+def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, use_graph=True, batch_prefill=True):
     from streaming_vlm_b200.multi_stream import MultiStreamEngine
     geo = TINY
     w_cpu = synthetic.random_weights(geo, seed=0)
@@ -23,6 +23,7 @@ def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, 
     oracles = [Session(w_cpu, geo.as_dict(), window, text_round, sink, sliding, suppress=suppress) for _ in range(n_streams)]
     multi = MultiStreamEngine({k: v.clone() for k, v in w_cpu.items()}, geo, n_streams, capacity=4096, window_size=window,
                               text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress, use_graph=use_graph)
+    multi.batch_prefill = batch_prefill
     n_vis = (height // 28) * (width // 28)
     mismatches = total = 0
     prev_len = [0] * n_streams
@@ -52,8 +53,10 @@ def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, 
     return mismatches, total, multi
 
 
-def test_three_streams_small_windows():
-    mism, total, multi = _run(3, 12, 112, 112, 4, 4, 16, 24)
+@pytest.mark.parametrize("batch_prefill", [True, False])
+def test_three_streams_small_windows(batch_prefill):
+    """batch_prefill=True: ViT and chunk prefill of all streams in one pass; False: per stream (the single-stream path)."""
+    mism, total, multi = _run(3, 12, 112, 112, 4, 4, 16, 24, batch_prefill=batch_prefill)
     assert all(e.cache.compactions >= 6 for e in multi.engines)
     assert len({tuple(e.prev_ids.tolist()) for e in multi.engines}) == 3          # the streams really differ
     assert mism <= max(2, total // 20), (mism, total)
