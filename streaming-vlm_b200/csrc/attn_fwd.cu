@@ -414,18 +414,35 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
     if (lane == 0) red[warp] = l_loc;
     __syncthreads();
     const float L = red[0] + red[1] + red[2] + red[3];
-    if (d >= D) return;
-    float acc = 0.f;
-    const float* src = part_o + (int64_t)r * D + d;
-    const int64_t stride = (int64_t)rows * D;
-    for (int s0 = 0; s0 < num_splits; s0 += 16) {       // 16 independent loads in flight per thread
-        float v[16];
+    // column sums: warp w takes splits w, w + 4, ...; a lane owns 4 adjacent columns (16-byte loads).  Up to 12 independent
+    // loads in flight per thread, so 48 splits cost ONE round trip to L2; the four partial sums meet in shared memory.
+    __shared__ float4 part_acc[4][32];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c4 = lane * 4;
+    if (c4 < D) {
+        const float* src = part_o + (int64_t)r * D + c4;
+        const int64_t stride = (int64_t)rows * D;
+        for (int s0 = warp; s0 < num_splits; s0 += 48) {
+            float4 v[12];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = (s0 + u < num_splits) ? __ldcg(src + (s0 + u) * stride) : 0.f;
+            for (int u = 0; u < 12; ++u) {
+                const int s = s0 + 4 * u;
+                v[u] = s < num_splits ? __ldcg(reinterpret_cast<const float4*>(src + s * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc += (s0 + u < num_splits ? w_s[s0 + u] : 0.f) * v[u];
+            for (int u = 0; u < 12; ++u) {
+                const int s = s0 + 4 * u;
+                const float w = s < num_splits ? w_s[s] : 0.f;
+                acc.x += w * v[u].x; acc.y += w * v[u].y; acc.z += w * v[u].z; acc.w += w * v[u].w;
+            }
+        }
     }
-    out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? acc / L : 0.f));
+    part_acc[warp][lane] = acc;
+    __syncthreads();
+    if (d >= D) return;
+    const float* pa = reinterpret_cast<const float*>(part_acc);
+    const float sum = pa[0 * 128 + d] + pa[1 * 128 + d] + pa[2 * 128 + d] + pa[3 * 128 + d];
+    out[(int64_t)r * D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(L > 0.f ? sum / L : 0.f));
 }
 
 // Merge for FEW splits and MANY rows (chunk prefill: 2-4 splits x Tq*Hq rows): one thread per (row, 4 columns), fully

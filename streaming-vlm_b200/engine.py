@@ -417,10 +417,10 @@ class StreamingEngine:
         c = self.cache
         if c.seq_len + 1 > c.capacity:
             raise RuntimeError(f"arena capacity {c.capacity} exceeded during decode")
-        # split count for the current cache length: ~3 key tiles per CTA keeps the serial TMA->UMMA->softmax chain short
-        # without drowning the merge kernel in partials (swept in benchmarks/microbench.py); capped by the workspace
+        # split count for the current cache length: ~2 key tiles per CTA keeps the serial TMA->UMMA->softmax chain short, at most
+        # one wave of CTAs; the merge kernel takes up to 48 partials in one L2 round trip (swept in benchmarks/microbench.py)
         n_tiles = (c.seq_len + 128) // 128
-        self._splits_now = max(1, min(self.decode_splits, -(-n_tiles // 3)))
+        self._splits_now = max(1, min(self.decode_splits, 148 // self.geo.num_kv_heads, -(-n_tiles // 2)))
         if self.use_graph:
             gr = self._graphs.get((c.cur, self._splits_now))
             if gr is None:
