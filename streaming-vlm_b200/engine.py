@@ -14,9 +14,11 @@ This is the B200-native counterpart of the reference's `streaming_inference` chu
 * lm_head runs on the last position only (the reference computes all and samples `[:, -1]`);
 * each decode step is one CUDA-graph replay (kv length and next position live in device memory).
 
-Dense projections go through cuBLAS (`torch.nn.functional.linear`); every other op on the path is a
-kernel of `libsvlm_b200.so`.  Section timers mirror the reference's PKV / GEN (`inference.py:312-329,
-422-452`).
+The dense projections of the ViT and of the chunk prefill go through cuBLAS (`torch.nn.functional.linear`);
+every other op on the path -- frame ingest, eviction, positions, appends, attention, the patch merger and the
+whole decode forward (weight-streaming GEMVs with fused norm / bias / rotation / append / SwiGLU / residual /
+argmax) -- is a kernel of `libsvlm_b200.so`.  Section timers mirror the reference's PKV / GEN
+(`inference.py:312-329, 422-452`).
 """
 from __future__ import annotations
 
