@@ -528,3 +528,50 @@ def test_frames_to_patches_bit_exact(abi, golden_dir):
         abi.frames_to_patches(torch.zeros(2, 30, 56, 3, dtype=torch.uint8, device=DEV))
     with pytest.raises(RuntimeError, match="temporal_patch"):
         abi.frames_to_patches(torch.zeros(3, 56, 56, 3, dtype=torch.uint8, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ against the reference's own attention library
+def _flash_attn():
+    try:
+        from flash_attn import flash_attn_func, flash_attn_varlen_func
+        return flash_attn_func, flash_attn_varlen_func
+    except Exception:        # noqa: BLE001  (library not in the image)
+        return None, None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Tq,S,splits", [(276, 5619, 2), (300, 5789, 1), (1, 5343, 16), (1, 40000, 37), (130, 700, 1)])
+def test_attn_causal_matches_flash_attn(abi, Tq, S, splits):
+    """The reference's attention path, run as the reference runs it (`repeat_kv` x7, `flash_attn_func(causal=True)`: bottom-right
+    aligned, scale 1/sqrt(128); language_forward.py:199-252) on the same K_rot / V: outputs agree within the bf16 tolerance."""
+    flash_attn_func, _ = _flash_attn()
+    if flash_attn_func is None:
+        pytest.skip("flash_attn is not installed")
+    Hq, H, L = 28, 4, 1
+    cap = ((S + 127) // 128) * 128 + 128
+    _, arena_dev, view = make_arena(abi, L, H, cap, seed=S)
+    q = torch.randn(Tq, Hq, 128, generator=torch.Generator().manual_seed(Tq)).to(torch.bfloat16).to(DEV)
+    out = torch.zeros_like(q)
+    ws = torch.zeros(abi.attn_workspace_bytes(Tq, Hq, 128, splits) // 4 + 16, dtype=torch.float32, device=DEV) if splits > 1 else None
+    abi.attn_causal(view, 0, 0, q, out, Tq, Hq, S, 1.0 / math.sqrt(128), splits, ws)
+    k = arena_dev[0, 1, 0, :, :S].transpose(0, 1).repeat_interleave(Hq // H, dim=1)[None].contiguous()      # [1, S, Hq, D]
+    v = arena_dev[0, 2, 0, :, :S].transpose(0, 1).repeat_interleave(Hq // H, dim=1)[None].contiguous()
+    ref = flash_attn_func(q[None], k, v, causal=True)[0]
+    torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), **ATT_TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cu", [list(range(0, 1025, 64)), [0, 1024], [0, 64, 100, 228, 300]])
+def test_vit_attn_matches_flash_attn_varlen(abi, cu):
+    """ViT attention against `flash_attn_varlen_func` (vision_forward.py:32-35) on the same rotated q, k and v."""
+    _, flash_attn_varlen_func = _flash_attn()
+    if flash_attn_varlen_func is None:
+        pytest.skip("flash_attn is not installed")
+    heads, D, n = 16, 80, cu[-1]
+    qkv = torch.randn(n, 3, heads, D, generator=torch.Generator().manual_seed(n)).to(torch.bfloat16).to(DEV)
+    out = torch.zeros(n, heads, D, dtype=torch.bfloat16, device=DEV)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=DEV)
+    abi.vit_attn(qkv, cu_t, out, n, heads, D, D ** -0.5)
+    max_len = max(b - a for a, b in zip(cu[:-1], cu[1:]))
+    ref = flash_attn_varlen_func(qkv[:, 0].contiguous(), qkv[:, 1].contiguous(), qkv[:, 2].contiguous(), cu_t, cu_t, max_len, max_len)
+    torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), **ATT_TOL)
