@@ -131,6 +131,8 @@ class StreamingEngine:
         self.kv_after_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tok_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.tok_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._tok_ring = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._tok_events = [torch.cuda.Event() for _ in range(2)]
         self._graphs = {}
         self._dec_qkv = torch.zeros((g.num_heads + 2 * g.num_kv_heads) * g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_q = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
@@ -469,6 +471,39 @@ class StreamingEngine:
         seq = list(ids_full)
         n_fwd = 1
         self.last_argmax = []
+        if forced is None and self.use_graph:
+            # Greedy loop with one step of look-ahead: the next decode step is enqueued BEFORE the host has seen the current
+            # token, so the GPU never idles on the device->host round trip.  The token copy is stream-ordered ahead of the
+            # step that overwrites `tok_dev`.  If the token turns out to be <|im_end|>, the speculated step is rolled back:
+            # its K/V row lies beyond the live length (never read), only the counters are restored.
+            pinned = self._tok_ring
+            speculated = False
+            while True:
+                slot = len(self.last_argmax) & 1
+                pinned[slot].copy_(self.tok_dev, non_blocking=True)
+                ev = self._tok_events[slot]
+                ev.record()
+                will_be_last = len(seq) + 1 - input_len >= self.max_new_tokens     # the token being read fills the budget
+                if not will_be_last and c.seq_len + 1 <= c.capacity:
+                    self.decode_step()
+                    speculated = True
+                else:
+                    speculated = False
+                ev.synchronize()
+                tok = int(pinned[slot][0])
+                self.last_argmax.append(tok)
+                seq.append(tok)
+                if tok == IM_END or will_be_last:
+                    if speculated:                      # undo the step that consumed the end token
+                        c.seq_len -= 1
+                        c._seen_tokens -= 1
+                        c.next_pos.sub_(1)
+                    break
+                if not speculated:
+                    self.decode_step()                  # raises the capacity error
+                n_fwd += 1
+            self._mark("decode_end")
+            return seq, n_fwd
         while True:
             self.tok_pinned.copy_(self.tok_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()

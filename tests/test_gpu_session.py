@@ -111,3 +111,30 @@ def test_tiny_stream_append_position_mode():
     assert int(engine.cache.next_pos) == oracle.pos_state["last_cache_position"] + 1
     assert int(engine.cache.next_pos) > 2 * engine.cache.seq_len          # positions really outgrew the cache
     assert mism <= max(2, total // 20), (mism, total)
+
+
+def test_lookahead_decode_equals_plain_loop():
+    """The greedy loop with one step of look-ahead (next decode step enqueued before the host has seen the current token,
+    rolled back when that token is <|im_end|>) produces the same stream as the plain read-then-step loop.  The vocabulary is
+    narrowed to four ids incl. <|im_end|> so that turns end early all the time; both position modes."""
+    from streaming_vlm_b200.engine import IM_END, StreamingEngine
+    geo = TINY
+    w_cpu = synthetic.random_weights(geo, seed=0)
+    suppress = torch.ones(geo.vocab, dtype=torch.bool)
+    suppress[torch.tensor([IM_END, 1000, 1001, 1002])] = False
+    for pos_mode in ("shrink", "append"):
+        engines = [StreamingEngine({k: v.clone() for k, v in w_cpu.items()}, geo, capacity=4096, window_size=4, text_round=4, text_sink=16,
+                                   text_sliding_window=24, suppress=suppress, use_graph=ug, pos_mode=pos_mode) for ug in (True, False)]
+        early = 0
+        for i in range(14):
+            px, grid = synthetic.patchify(synthetic.frames(i, 112, 112), geo)
+            prompt = synthetic.round_prompt(i, 16, 6)
+            ra, rb = (e.step(prompt, px.to("cuda"), grid) for e in engines)
+            assert ra["ids"] == rb["ids"], f"{pos_mode} chunk {i}"
+            assert ra["cache_len"] == rb["cache_len"] and ra["runs"] == rb["runs"], f"{pos_mode} chunk {i}"
+            assert int(engines[0].cache.next_pos) == int(engines[1].cache.next_pos), f"{pos_mode} chunk {i}: next position"
+            early += len(ra["new_tokens"]) < engines[0].max_new_tokens
+        assert early >= 3, "the test stream never ended a turn early"
+        n = engines[0].cache.seq_len
+        a, b = (e.cache.arena[e.cache.cur, :, :, :, :n] for e in engines)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"{pos_mode}: arenas differ"
