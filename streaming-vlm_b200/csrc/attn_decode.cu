@@ -121,7 +121,6 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
     const uint32_t tmem = sh->tmem_base;
     // everything above (barriers, TMEM, zeroed P^T) overlapped the tail of the QKV kernel; q, the new arena row and the
     // device-side length are its outputs
-    pdl_trigger();
     pdl_wait();
 
     const int kv_len = p.kv_len_dev[strm] ? __ldg(p.kv_len_dev[strm]) : p.kv_len;
@@ -287,6 +286,7 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
         }
 
         // ---- epilogue: total row sums (one reduction), then O^T lanes
+        pdl_trigger();
         float l_tot[G];
 #pragma unroll
         for (int h = 0; h < G; ++h) {
@@ -345,7 +345,7 @@ static int launch_decode_s(const DecMaps& maps, const DecParams& p, dim3 grid, c
         }
         attr_done = true;
     }
-    launch_pdl(attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, maps, p);
+    launch_pdl(PDL_OTHER, attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, maps, p);
     return launch_status("attn_decode_kernel");
 }
 
@@ -415,7 +415,7 @@ static int decode_launch_common(const svlm_arena_t* geom, const void* const* are
     if (num_splits > 1) {
         // A separate merge launch beats an in-kernel "last CTA merges" epilogue here (measured: 10.2 vs 12.6 us per layer at
         // 4k keys, 30.1 vs 33.7 us at 64k): one-head CTAs finish the merge in one load latency.
-        launch_pdl(attn_combine_kernel, dim3(p.rows_total), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out,
+        launch_pdl(PDL_OTHER, attn_combine_kernel, dim3(p.rows_total), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out,
                    p.rows_total, D, num_splits);
         return launch_status("attn_combine_kernel");
     }

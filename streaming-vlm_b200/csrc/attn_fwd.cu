@@ -384,7 +384,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // and the per-split weights live in shared memory, so the column loop issues independent loads.
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
                                                             uint16_t* __restrict__ out, int rows, int D, int num_splits) {
-    pdl_trigger();
     pdl_wait();
     __shared__ float w_s[256];
     __shared__ float l_s[256];

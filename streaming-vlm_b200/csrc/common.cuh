@@ -44,22 +44,25 @@ inline int launch_status(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------ programmatic dependent launch
-// The decode step is a chain of ~170 short kernels per token.  Kernels launched through launch_pdl() may start while
-// their predecessor in the stream is still draining: everything before pdl_wait() (barrier/TMEM setup, prefetch of
-// immutable weights) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and
-// its writes are visible, so all reads of mutable data and all writes come after it.  OFF by default (the device-side
-// instructions are then no-ops): measured on B200 it LOSES 7 ms per chunk (70.8 vs 63.9 ms) -- successor CTAs parked at
-// the wait take SM slots from the weight-streaming GEMVs.  SVLM_PDL=1 enables the attribute for experiments.
-inline bool pdl_enabled() {
+// The decode step is a chain of ~170 short kernels per token.  Kernels launched through launch_pdl() may become resident
+// while their predecessor in the stream is still draining: everything before pdl_wait() (barrier / TMEM set-up, row
+// pointers, L2 prefetch of immutable weights) overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has completed and its writes are visible, so all reads of mutable data and all writes come after it.  A kernel
+// calls pdl_trigger() when its own bulk work is done (after the weight stream / the key-tile loop): measured on B200,
+// triggering at kernel START loses 7 ms per chunk (successor CTAs parked at the wait take SM slots from the
+// weight-streaming GEMVs), triggering late gains 2.7-3 % (32.6 -> 33.4 frames/s).
+// SVLM_PDL: 1 = every decode-chain kernel (default), 0 = off, 2 = only the GEMVs, 3 = only attention / merge / finalize
+enum { PDL_GEMV = 1, PDL_OTHER = 2 };
+inline bool pdl_enabled(int kind) {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SVLM_PDL");
-        v = (e && e[0] == '1') ? 1 : 0;
+        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1;
     }
-    return v != 0;
+    return v == 1 || (v == 2 && kind == PDL_GEMV) || (v == 3 && kind == PDL_OTHER);
 }
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -69,7 +72,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors are picked up by launch_status()
 }
 #ifdef __CUDACC__

@@ -70,7 +70,37 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
     __shared__ unsigned long long best[GROUPS * RG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = p.K;
-    pdl_trigger();      // programmatic dependent launch: the successor's CTAs may become resident while this grid runs
+    // ---- row pointers (immutable weights): resolved, and the first batch pulled towards L2, BEFORE the grid dependency resolves --
+    // with programmatic dependent launch this CTA may already be resident while the predecessor kernel drains
+    const int grp = warp / KS, ks = warp % KS;
+    const int n0 = (blockIdx.x * GROUPS + grp) * RG;
+    const uint16_t* rows[NR];
+    if (MODE == GEMV_QKV) {
+        // group index -> (head, j): rows head*128 + j and head*128 + 64 + j, the two halves mRoPE mixes
+        const int gidx = min(blockIdx.x * GROUPS + grp, p.N / 2 - 1);
+        const int n = (gidx >> 6) * 128 + (gidx & 63);
+        rows[0] = p.W + (int64_t)n * K;
+        rows[NR - 1] = p.W + (int64_t)(n + 64) * K;
+    } else {
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            const int n = min(n0 + r, p.N - 1);
+            rows[r] = p.W + (int64_t)n * K;
+            if (MODE == GEMV_SWIGLU) rows[RG + r] = p.W + (int64_t)(p.N + n) * K;
+        }
+    }
+    const int steps = (K + 255) >> 8;
+    const int s_begin = steps * ks / KS, s_end = steps * (ks + 1) / KS;
+    if (s_begin < s_end) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = ((s_begin + u) << 8) + lane * 8;
+            if (s_begin + u < s_end && k < K) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows[r] + k));
+            }
+        }
+    }
     pdl_wait();         // x / residual are the predecessor's outputs
 
     // ---- prologue: stage x (RMS-normalised when norm_w is given) in shared memory; plain/residual GEMVs without a
@@ -110,28 +140,9 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
     }
 
     // ---- body
-    const int grp = warp / KS, ks = warp % KS;
-    const int n0 = (blockIdx.x * GROUPS + grp) * RG;
-    const uint16_t* rows[NR];
-    if (MODE == GEMV_QKV) {
-        // group index -> (head, j): rows head*128 + j and head*128 + 64 + j, the two halves mRoPE mixes
-        const int gidx = min(blockIdx.x * GROUPS + grp, p.N / 2 - 1);
-        const int n = (gidx >> 6) * 128 + (gidx & 63);
-        rows[0] = p.W + (int64_t)n * K;
-        rows[NR - 1] = p.W + (int64_t)(n + 64) * K;
-    } else {
-#pragma unroll
-        for (int r = 0; r < RG; ++r) {
-            const int n = min(n0 + r, p.N - 1);
-            rows[r] = p.W + (int64_t)n * K;
-            if (MODE == GEMV_SWIGLU) rows[RG + r] = p.W + (int64_t)(p.N + n) * K;
-        }
-    }
     float acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.f;
-    const int steps = (K + 255) >> 8;
-    const int s_begin = steps * ks / KS, s_end = steps * (ks + 1) / KS;
     for (int s0 = s_begin; s0 < s_end; s0 += U) {
         uint4 w[U][NR], xv[U];
 #pragma unroll
@@ -149,6 +160,7 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
             for (int r = 0; r < NR; ++r) acc[r] += dot8(w[u][r], xv[u]);
         }
     }
+    pdl_trigger();      // the weight stream of this CTA is done: the successor's CTAs may start to become resident
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
 #pragma unroll
@@ -280,7 +292,7 @@ static int launch_gemv(const GemvParams& p, cudaStream_t st) {
     }
     const int rows_per_cta = (8 / KS) * RG;
     const int grid = (p.N + rows_per_cta - 1) / rows_per_cta;      // QKV: RG = 2 -> one group per (n, n+64) pair, same count
-    launch_pdl(gemv_kernel<MODE, RG, KS, U, STAGE>, dim3(grid), dim3(GEMV_THREADS), smem, st, p);
+    launch_pdl(PDL_GEMV, gemv_kernel<MODE, RG, KS, U, STAGE>, dim3(grid), dim3(GEMV_THREADS), smem, st, p);
     return launch_status("gemv_kernel");
 }
 
@@ -373,7 +385,7 @@ extern "C" int svlm_lm_head_argmax(const void* W, const void* x, const void* nor
     GemvParams p{(const uint16_t*)W, (const uint16_t*)x, (const uint16_t*)norm_weight, eps, nullptr, nullptr, nullptr, N, K, suppress,
                  (unsigned long long*)key_scratch};
     if ((rc = dispatch_rw<GEMV_ARGMAX>(p, (cudaStream_t)stream))) return rc;
-    launch_pdl(decode_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
+    launch_pdl(PDL_OTHER, decode_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
     return launch_status("decode_finalize_kernel");
 }
 

@@ -59,7 +59,7 @@ class MultiStreamEngine:
         self.ws = torch.zeros(_abi.attn_workspace_bytes(B, g.num_heads, g.head_dim, self.max_splits) // 4 + 16, dtype=torch.float32,
                               device=dev)
         self._graphs, self._slots = {}, {}
-        self._pf_graphs = {}
+        self._pf_graphs, self._pf_seen, self._pf_calls = {}, {}, 0
         self._pf_ids = torch.zeros(B * 1024, dtype=torch.int64, device=dev)
         self.batch_prefill = True      # ViT and chunk prefill of all streams in one pass (one weight sweep); False = per stream
         self.use_graph = first.use_graph
@@ -194,7 +194,12 @@ class MultiStreamEngine:
         entry = self._pf_graphs.get(key) if self.use_graph else None
         if entry is None:
             last = torch.tensor([o_ + t - 1 for o_, t, _, _ in metas], dtype=torch.long, device=self.device)
-            if not self.use_graph:
+            # A layout (new-token counts of all streams) is captured when it shows up during start-up or for the second time: a
+            # stream that ends one turn early produces a one-off layout, and capturing that would cost far more than running it
+            # eagerly once.
+            self._pf_calls += 1
+            self._pf_seen[key] = self._pf_seen.get(key, 0) + 1
+            if not self.use_graph or (self._pf_calls > 4 and self._pf_seen[key] < 2):
                 self._prefill_body(ids, metas, video, last)
             else:
                 side = torch.cuda.Stream()
