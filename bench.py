@@ -257,7 +257,9 @@ def kernel_rooflines(engine, pk):
     att = torch.randn(hq * d, device=dev).to(torch.bfloat16)
     act = torch.empty(g.mlp, dtype=torch.bfloat16, device=dev)
     for name, fn, nbytes in [
-        ("gemv_norm_qkv", lambda Lw: _abi.gemv_bf16(Lw["wqkv"], x, qkv_o, 0, Lw["ln1"], g.rms_eps, Lw["bqkv"]), engine.layers[0]["wqkv"].numel() * 2),
+        ("gemv_norm_qkv_rope_append", lambda Lw: _abi.gemv_qkv_rope_append(c.view, c.cur, 0, Lw["wqkv"], x, Lw["ln1"], g.rms_eps, Lw["bqkv"], hq, q1,
+                                                                             engine.kv_len_dev, c.next_pos, c.cos_table, c.sin_table),
+         engine.layers[0]["wqkv"].numel() * 2),
         ("gemv_o_residual", lambda Lw: _abi.gemv_bf16(Lw["wo"], att, xr, 1, residual=xr), engine.layers[0]["wo"].numel() * 2),
         ("gemv_norm_gate_up_swiglu", lambda Lw: _abi.gemv_bf16(Lw["wgu"], x, act, 2, Lw["ln2"], g.rms_eps), engine.layers[0]["wgu"].numel() * 2),
         ("gemv_down_residual", lambda Lw: _abi.gemv_bf16(Lw["wd"], act, xr, 1, residual=xr), engine.layers[0]["wd"].numel() * 2),
