@@ -448,7 +448,7 @@ def run_gpu(args):
         dom = max(roofs, key=lambda k: roofs[k]["share_ms_per_step"])
         roof = {k: roofs[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
         roof["kernel"] = dom
-        roof["peak_source"] = pk["source"]
+        roof["peak_source"] = pk["source"] + "; HBM peak = measured COPY bandwidth (read + write), read-only streams can slightly exceed it"
         line = {"metric": METRIC, "value": world * args.steps * FRAMES_PER_CHUNK / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
