@@ -101,8 +101,38 @@ def patch_merger(x, w, pfx="model.visual.merger.", unit=4):
     return F.linear(h, w[pfx + "mlp.2.weight"], w[pfx + "mlp.2.bias"])
 
 
+def vision_forward_qwen2(pixels, grid_thw, w, geo):
+    """The Qwen2-VL tower the reference's `inference/qwen2/vision_forward.py:57-80` drives (HF
+    `Qwen2VisionTransformerPretrainedModel`): patch embed -> 2-D rotary -> blocks of LayerNorm + full attention per frame +
+    LayerNorm + fc1 / quick-GELU / fc2 -> `PatchMerger` (LayerNorm -> view [N/4, 4C] -> Linear -> GELU(erf) -> Linear).
+    No window reordering.  Pinned against the HF module itself in tests/test_oracle_golden.py."""
+    pfx = "model.visual."
+    unit = geo["spatial_merge_size"] ** 2
+    wt = w[pfx + "patch_embed.proj.weight"]
+    x = F.linear(pixels.to(wt.dtype), wt.reshape(wt.shape[0], -1))
+    head_dim = geo["vit_hidden"] // geo["vit_heads"]
+    cos, sin = vision_rotary(grid_thw, head_dim, geo["spatial_merge_size"])
+    full = [0]
+    for t, h, ww in grid_thw:
+        for _ in range(t):
+            full.append(full[-1] + h * ww)
+    cu = torch.tensor(full, dtype=torch.int32)
+    ln = lambda t_, name: F.layer_norm(t_, (t_.shape[-1],), w[name + ".weight"], w[name + ".bias"], 1e-6)
+    for li in range(geo["vit_depth"]):
+        b = f"{pfx}blocks.{li}."
+        x = x + vit_attention(ln(x, b + "norm1"), w, b + "attn.", geo["vit_heads"], cu, cos, sin)
+        h1 = F.linear(ln(x, b + "norm2"), w[b + "mlp.fc1.weight"], w[b + "mlp.fc1.bias"])
+        x = x + F.linear(h1 * torch.sigmoid(1.702 * h1), w[b + "mlp.fc2.weight"], w[b + "mlp.fc2.bias"])      # QuickGELU
+    m = pfx + "merger."
+    y = ln(x, m + "ln_q").view(-1, x.shape[-1] * unit)
+    y = F.gelu(F.linear(y, w[m + "mlp.0.weight"], w[m + "mlp.0.bias"]))
+    return F.linear(y, w[m + "mlp.2.weight"], w[m + "mlp.2.bias"])
+
+
 def vision_forward(pixels, grid_thw, w, geo, return_hidden=False, timers=None):
     """pixels [N, C*Tp*P*P], grid_thw list of (t,h,w) -> merged tokens [N/4, out_hidden]."""
+    if geo.get("vit_kind", "qwen2_5") == "qwen2":
+        return vision_forward_qwen2(pixels, grid_thw, w, geo)
     pfx = "model.visual."
     unit = geo["spatial_merge_size"] ** 2
     wt = w[pfx + "patch_embed.proj.weight"]

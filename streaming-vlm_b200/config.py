@@ -34,6 +34,7 @@ class Geometry:
     fullatt_block_indexes: tuple = (7, 15, 23, 31)
     tokens_per_second: int = 2
     in_channels: int = 3
+    vit_kind: str = "qwen2_5"       # "qwen2": the Qwen2-VL tower (LayerNorm, fc1/quick-GELU/fc2, every block full attention)
 
     @property
     def group(self) -> int:
@@ -66,15 +67,23 @@ PRESETS = {"tiny": TINY, "7b": QWEN25VL_7B, "32b": QWEN25VL_32B}
 
 
 def from_hf_config(cfg) -> Geometry:
-    """Geometry of a transformers `Qwen2_5_VLConfig` (HF 5.x field names)."""
+    """Geometry of a transformers `Qwen2_5_VLConfig` or `Qwen2VLConfig` (HF 5.x field names)."""
     t, v = cfg.text_config, cfg.vision_config
     rp = getattr(t, "rope_parameters", None) or getattr(t, "rope_scaling", None) or {}
+    text = dict(hidden=t.hidden_size, num_layers=t.num_hidden_layers, num_heads=t.num_attention_heads,
+                num_kv_heads=t.num_key_value_heads, head_dim=t.hidden_size // t.num_attention_heads,
+                mlp=t.intermediate_size, vocab=t.vocab_size, rope_theta=float(rp.get("rope_theta", 1e6)),
+                mrope_section=tuple(rp.get("mrope_section", (16, 24, 24))), rms_eps=t.rms_norm_eps)
+    name = getattr(cfg, "name_or_path", "") or "hf"
+    if hasattr(v, "embed_dim"):
+        # Qwen2-VL: `embed_dim` is the tower width (`hidden_size` is the merger's output width), no windows, and the temporal
+        # position of a vision token is its frame-pair index (no tokens_per_second scaling: qwen2/pos_emb.py)
+        return Geometry(name=name, **text, vit_depth=v.depth, vit_hidden=v.embed_dim, vit_heads=v.num_heads,
+                        vit_mlp=int(v.embed_dim * v.mlp_ratio), patch_size=v.patch_size, temporal_patch_size=v.temporal_patch_size,
+                        spatial_merge_size=v.spatial_merge_size, window_size=0, fullatt_block_indexes=tuple(range(v.depth)),
+                        tokens_per_second=1, in_channels=getattr(v, "in_channels", 3), vit_kind="qwen2")
     return Geometry(
-        name=getattr(cfg, "name_or_path", "") or "hf",
-        hidden=t.hidden_size, num_layers=t.num_hidden_layers, num_heads=t.num_attention_heads,
-        num_kv_heads=t.num_key_value_heads, head_dim=t.hidden_size // t.num_attention_heads,
-        mlp=t.intermediate_size, vocab=t.vocab_size, rope_theta=float(rp.get("rope_theta", 1e6)),
-        mrope_section=tuple(rp.get("mrope_section", (16, 24, 24))), rms_eps=t.rms_norm_eps,
+        name=name, **text,
         vit_depth=v.depth, vit_hidden=v.hidden_size, vit_heads=v.num_heads, vit_mlp=v.intermediate_size,
         patch_size=v.patch_size, temporal_patch_size=v.temporal_patch_size,
         spatial_merge_size=v.spatial_merge_size, window_size=v.window_size,

@@ -12,24 +12,34 @@ from streaming_vlm_b200.config import from_hf_config
 pytestmark = pytest.mark.gpu
 
 
-def test_patched_hf_model_matches_oracle():
-    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+def _tiny_model(family):
+    text = dict(hidden_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, intermediate_size=1024,
+                vocab_size=152064, rms_norm_eps=1e-6, rope_parameters={"rope_type": "default", "rope_theta": 1e6, "mrope_section": [16, 24, 24]})
+    if family == "qwen2_5":
+        from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+        from streaming_vlm_b200.inference.qwen2_5.patch_model import convert_qwen2_5_to_streaming as convert
+        cfg = Qwen2_5_VLConfig(text_config=text, vision_config=dict(depth=4, hidden_size=320, num_heads=4, intermediate_size=640, out_hidden_size=512,
+                                                                    fullatt_block_indexes=[1, 3], tokens_per_second=2))
+        return cfg, Qwen2_5_VLForConditionalGeneration(cfg), convert
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    from streaming_vlm_b200.inference.qwen2.patch_model import convert_qwen2_to_streaming as convert
+    cfg = Qwen2VLConfig(text_config=text, vision_config=dict(depth=3, embed_dim=320, num_heads=4, mlp_ratio=2, hidden_size=512))
+    return cfg, Qwen2VLForConditionalGeneration(cfg), convert
+
+
+@pytest.mark.parametrize("family", ["qwen2_5", "qwen2"])
+def test_patched_hf_model_matches_oracle(family):
+    """`convert_qwen2_5_to_streaming` (qwen2_5/patch_model.py:18-38) and `convert_qwen2_to_streaming` (qwen2/patch_model.py)."""
     from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
     from streaming_vlm_b200.inference.inference import process_past_kv
-    from streaming_vlm_b200.inference.qwen2_5.patch_model import convert_qwen2_5_to_streaming
     from streaming_vlm_b200.inference.streaming_args import StreamingArgs
     torch.manual_seed(0)
-    cfg = Qwen2_5_VLConfig(
-        text_config=dict(hidden_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, intermediate_size=1024,
-                         vocab_size=152064, rms_norm_eps=1e-6,
-                         rope_parameters={"rope_type": "default", "rope_theta": 1e6, "mrope_section": [16, 24, 24]}),
-        vision_config=dict(depth=4, hidden_size=320, num_heads=4, intermediate_size=640, out_hidden_size=512,
-                           fullatt_block_indexes=[1, 3], tokens_per_second=2))
-    model = Qwen2_5_VLForConditionalGeneration(cfg).to(torch.bfloat16).eval()
+    cfg, model, convert = _tiny_model(family)
+    model = model.to(torch.bfloat16).eval()
     w_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     geo = from_hf_config(cfg)
-    assert geo.num_layers == 2 and geo.vit_depth == 4 and geo.tokens_per_second == 2
-    model = convert_qwen2_5_to_streaming(model.to("cuda"))
+    assert geo.num_layers == 2 and geo.vit_kind == family and geo.tokens_per_second == (2 if family == "qwen2_5" else 1)
+    model = convert(model.to("cuda"))
     sup = synthetic.suppress_mask(geo.vocab)
     win, tr, sink, slide = 2, 2, 8, 8
     oracle = Session(w_cpu, geo.as_dict(), win, tr, sink, slide, suppress=sup, max_new_tokens=5)

@@ -132,3 +132,29 @@ def test_frame_ingest_oracle_equals_hf_processor(golden_dir):
     got, grid = o_frames.frames_to_patches(fr)
     assert grid == (1, 32, 32) and got.shape == (1024, 1176)
     assert hashlib.sha256(got.numpy().tobytes()).digest() == bytes(z["full__sha256"])
+
+
+# ------------------------------------------------------------------------------------------------ Qwen2-VL variant (row f4)
+def test_qwen2_vl_tower_oracle_equals_hf_module():
+    """oracle/vit.py::vision_forward_qwen2 against transformers' own `Qwen2VisionTransformerPretrainedModel` (the module
+    the reference patches in `inference/qwen2/`), same random weights, fp32, on CPU."""
+    from transformers import Qwen2VLConfig
+    from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VisionTransformerPretrainedModel
+    from oracle import vit as o_vit
+    from streaming_vlm_b200 import synthetic
+    from streaming_vlm_b200.config import from_hf_config
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(text_config=dict(hidden_size=256, num_hidden_layers=1, num_attention_heads=2, num_key_value_heads=1, intermediate_size=256,
+                                         vocab_size=152064, rope_parameters={"rope_type": "default", "rope_theta": 1e6, "mrope_section": [16, 24, 24]}),
+                        vision_config=dict(depth=3, embed_dim=160, num_heads=2, mlp_ratio=2, hidden_size=256))
+    geo = from_hf_config(cfg)
+    assert geo.vit_kind == "qwen2" and geo.vit_hidden == 160 and geo.tokens_per_second == 1
+    tower = Qwen2VisionTransformerPretrainedModel._from_config(cfg.vision_config, attn_implementation="eager").float().eval()
+    w = {"model.visual." + k: v.detach().clone() for k, v in tower.state_dict().items()}
+    px, grid = synthetic.patchify(synthetic.frames(2, 112, 84, n=4), geo)               # two frame pairs, non-square
+    with torch.no_grad():
+        out = tower(px, torch.tensor([list(grid)]))
+    want = out.pooler_output if hasattr(out, "pooler_output") else out
+    got = o_vit.vision_forward(px, [grid], w, geo.as_dict())
+    assert got.shape == want.shape == (grid[0] * grid[1] * grid[2] // 4, 256)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
