@@ -228,12 +228,21 @@ int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slo
  * (inference/inference.py:390-395 -> HF Qwen2-VL video processor) for a clip that is already at its target size:
  * uint8 RGB frames [T][H][W][3] (decord's on-wire layout) -> ViT patch rows [gt*gh*gw][3*Tp*P*P] in merge-unit-major
  * order, normalised as (x - mean') / std' in fp32 with mean' = mean * 255, std' = std * 255 (HF's fused rescale +
- * normalise); out is fp32 or bf16 (the ViT's patch embedding consumes bf16).  The bicubic resize of
- * livecc_utils/video_process_patch.py:140-153 is NOT covered (sizes must be multiples of patch * merge).
+ * normalise); out is fp32 or bf16 (the ViT's patch embedding consumes bf16).  Sizes must be multiples of patch * merge
+ * (svlm_frames_resize_bicubic below brings a clip there).
  * ------------------------------------------------------------------------------------- */
 int svlm_frames_to_patches(const void* frames_thwc_u8, int n_frames, int height, int width, int patch, int temporal_patch,
                            int merge, const float* mean3_host, const float* std3_host, void* out, int out_is_bf16,
                            void* stream);
+
+/* Spatial resize in front of (9): `livecc_utils/.../video_process_patch.py:133-153` (`torchvision.transforms.functional.resize`
+ * with BICUBIC, antialias=True, on the uint8 clip; target size from `smart_resize`).  Separable anti-aliased bicubic, horizontal
+ * pass first into the fp32 scratch tmp_f32 [T][H][out_width][3], round-half-even + clamp at the end.  The tap tables (device
+ * pointers: first input index and tap count per output index, normalised weights [n_out][k]) are built by the caller the way
+ * ATen builds them (`streaming_vlm_b200/utils/frames.py::aa_bicubic_taps`). */
+int svlm_frames_resize_bicubic(const void* in_thwc_u8, int n_frames, int height, int width, void* out_thwc_u8, int out_height,
+                               int out_width, void* tmp_f32, const int32_t* x_start, const int32_t* x_count, const float* x_weights,
+                               int kx, const int32_t* y_start, const int32_t* y_count, const float* y_weights, int ky, void* stream);
 
 /* Scheduling aid of the decode loop (no reference counterpart: the reference leaves cache policy to the libraries it
  * calls): issues L2 prefetches for [ptr, ptr + bytes).  The session runner launches it on a side stream next to the

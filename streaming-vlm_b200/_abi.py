@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
-           "svlm_frames_to_patches",
+           "svlm_frames_to_patches", "svlm_frames_resize_bicubic",
            "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
@@ -97,6 +97,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
+    L.svlm_frames_resize_bicubic.argtypes = [vp, c_int, c_int, c_int, vp, c_int, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp]
     L.svlm_frames_to_patches.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), vp, c_int, vp]
     L.svlm_qkv_rope_append_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int,
                                                vp, vp, vp, c_int, i32p, vp]
@@ -290,6 +291,29 @@ def frames_to_patches(frames_thwc, out=None, patch=14, temporal_patch=2, merge=2
     check(lib().svlm_frames_to_patches(frames_thwc.data_ptr(), t, h, w, patch, temporal_patch, merge, (c_float * 3)(*m), (c_float * 3)(*s_),
                                        out.data_ptr(), 1 if out.dtype == torch.bfloat16 else 0, _stream()), "svlm_frames_to_patches")
     return out, grid
+
+
+_TAP_CACHE = {}
+
+
+def frames_resize_bicubic(frames_thwc, out_h: int, out_w: int):
+    """uint8 CUDA clip [T, H, W, 3] -> uint8 [T, out_h, out_w, 3], anti-aliased bicubic (torchvision `resize(BICUBIC, antialias=True)`)."""
+    from .utils.frames import aa_bicubic_taps
+    _req_cuda(frames_thwc)
+    assert frames_thwc.dtype == torch.uint8 and frames_thwc.dim() == 4 and frames_thwc.shape[-1] == 3 and frames_thwc.is_contiguous()
+    t, h, w, _ = frames_thwc.shape
+    dev = frames_thwc.device
+    key = (h, w, out_h, out_w, str(dev))
+    taps = _TAP_CACHE.get(key)
+    if taps is None:
+        taps = _TAP_CACHE[key] = tuple(torch.from_numpy(a).to(dev) for a in (*aa_bicubic_taps(w, out_w), *aa_bicubic_taps(h, out_h)))
+    xs, xc, xw, ys, yc, yw = taps
+    tmp = torch.empty(t, h, out_w, 3, dtype=torch.float32, device=dev)
+    out = torch.empty(t, out_h, out_w, 3, dtype=torch.uint8, device=dev)
+    check(lib().svlm_frames_resize_bicubic(frames_thwc.data_ptr(), t, h, w, out.data_ptr(), out_h, out_w, tmp.data_ptr(), xs.data_ptr(),
+                                           xc.data_ptr(), xw.data_ptr(), xw.shape[1], ys.data_ptr(), yc.data_ptr(), yw.data_ptr(),
+                                           yw.shape[1], _stream()), "svlm_frames_resize_bicubic")
+    return out
 
 
 def prefetch_l2(t, nbytes=None):

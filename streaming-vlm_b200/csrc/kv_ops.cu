@@ -362,6 +362,63 @@ __global__ void __launch_bounds__(256) frames_to_patches_kernel(const uint8_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Anti-aliased bicubic resize of a clip (uint8 [T][H][W][3] -> uint8 [T][H2][W2][3]), separable: a horizontal pass into
+// fp32, then a vertical pass that rounds half-to-even and clamps.  Tap tables (first input index, tap count, normalised fp32
+// weights per output index) are built on the host exactly as ATen's `_upsample_bicubic2d_aa` builds them; accumulation is
+// sequential fp32 with separate multiply and add roundings (no FMA), so the result is a pure function of the tables.
+// ---------------------------------------------------------------------------------------------------
+struct ResizeTaps {
+    const int32_t* start;
+    const int32_t* count;
+    const float* weights;     // [n_out][k]
+    int k;
+};
+
+__global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict__ in, float* __restrict__ tmp, int rows, int W, int W2,
+                                                        const ResizeTaps tx) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // (row, x2); row = t * H + y
+    if (idx >= (int64_t)rows * W2) return;
+    const int x2 = (int)(idx % W2);
+    const int64_t row = idx / W2;
+    const int s0 = __ldg(tx.start + x2), n = __ldg(tx.count + x2);
+    const float* w = tx.weights + (int64_t)x2 * tx.k;
+    const uint8_t* src = in + (row * W + s0) * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < n; ++j) {
+        const float wj = __ldg(w + j);
+        a0 = __fadd_rn(a0, __fmul_rn(wj, (float)src[3 * j + 0]));
+        a1 = __fadd_rn(a1, __fmul_rn(wj, (float)src[3 * j + 1]));
+        a2 = __fadd_rn(a2, __fmul_rn(wj, (float)src[3 * j + 2]));
+    }
+    float* dst = tmp + idx * 3;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2;
+}
+
+__global__ void __launch_bounds__(256) resize_v_kernel(const float* __restrict__ tmp, uint8_t* __restrict__ out, int T, int H, int H2, int W2,
+                                                        const ResizeTaps ty) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // (t, y2, x2)
+    if (idx >= (int64_t)T * H2 * W2) return;
+    const int x2 = (int)(idx % W2);
+    const int y2 = (int)((idx / W2) % H2);
+    const int t = (int)(idx / ((int64_t)W2 * H2));
+    const int s0 = __ldg(ty.start + y2), n = __ldg(ty.count + y2);
+    const float* w = ty.weights + (int64_t)y2 * ty.k;
+    const float* src = tmp + (((int64_t)t * H + s0) * W2 + x2) * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < n; ++j) {
+        const float wj = __ldg(w + j);
+        const float* r = src + (int64_t)j * W2 * 3;
+        a0 = __fadd_rn(a0, __fmul_rn(wj, r[0]));
+        a1 = __fadd_rn(a1, __fmul_rn(wj, r[1]));
+        a2 = __fadd_rn(a2, __fmul_rn(wj, r[2]));
+    }
+    uint8_t* dst = out + idx * 3;
+    dst[0] = (uint8_t)fminf(fmaxf(rintf(a0), 0.f), 255.f);
+    dst[1] = (uint8_t)fminf(fmaxf(rintf(a1), 0.f), 255.f);
+    dst[2] = (uint8_t)fminf(fmaxf(rintf(a2), 0.f), 255.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // vit_rope: qkv [N][3][H][D] bf16, q and k rotated in place.  fp32 products and sum, no FMA contraction
 // (apply_rotary_pos_emb_flashatt semantics: q.float()*cos + rotate_half(q.float())*sin, cast back).
 // One thread = one 8-element chunk of the first half and its partner chunk in the second half.
@@ -616,6 +673,26 @@ extern "C" int svlm_frames_to_patches(const void* frames_thwc_u8, int n_frames, 
     const int64_t total2 = (int64_t)n_frames * height * width * 3 / 2;
     frames_to_patches_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames_thwc_u8, out, p);
     return launch_status("frames_to_patches_kernel");
+}
+
+extern "C" int svlm_frames_resize_bicubic(const void* in_thwc_u8, int n_frames, int height, int width, void* out_thwc_u8, int out_height,
+                                          int out_width, void* tmp_f32, const int32_t* x_start, const int32_t* x_count,
+                                          const float* x_weights, int kx, const int32_t* y_start, const int32_t* y_count,
+                                          const float* y_weights, int ky, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(in_thwc_u8 && out_thwc_u8 && tmp_f32, "NULL frame / scratch pointer");
+    SVLM_REQUIRE(x_start && x_count && x_weights && y_start && y_count && y_weights, "NULL tap table");
+    SVLM_REQUIRE(n_frames > 0 && height > 0 && width > 0 && out_height > 0 && out_width > 0, "bad frame geometry");
+    SVLM_REQUIRE(kx > 0 && ky > 0, "bad tap count");
+    ResizeTaps tx{x_start, x_count, x_weights, kx}, ty{y_start, y_count, y_weights, ky};
+    const int64_t n1 = (int64_t)n_frames * height * out_width, n2 = (int64_t)n_frames * out_height * out_width;
+    resize_h_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in_thwc_u8, (float*)tmp_f32,
+                                                                                    n_frames * height, width, out_width, tx);
+    if ((rc = launch_status("resize_h_kernel"))) return rc;
+    resize_v_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)tmp_f32, (uint8_t*)out_thwc_u8, n_frames,
+                                                                                    height, out_height, out_width, ty);
+    return launch_status("resize_v_kernel");
 }
 
 extern "C" int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int n_tokens, int heads, int head_dim, void* stream) {

@@ -115,6 +115,7 @@ class StreamingEngine:
             max_position = 1 << 17
         self.cache = StreamingCache(geo, capacity, self.device, max_position=max_position)
         self._pos_upper = 0          # host-side upper bound of the largest position handed out (append mode)
+        self.video_pixel_budget = (None, None)      # (min_pixels, max_pixels) per frame for `ingest`; None = keep sizes that fit the patch grid
         self.scale = 1.0 / math.sqrt(geo.head_dim)
         self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 296 // geo.num_kv_heads))   # two CTAs per SM
         self.prefill_splits = prefill_splits
@@ -612,6 +613,15 @@ class StreamingEngine:
         """uint8 RGB frames [T, H, W, 3] in HBM -> (bf16 patch rows for the ViT, grid): the pixel half of the reference's
         `processor(text=..., videos=clip)` call (inference.py:390-395) for a clip already at its target size."""
         g = self.geo
+        factor = g.patch_size * g.spatial_merge_size
+        t, h, w, _ = frames_thwc.shape
+        lo, hi = self.video_pixel_budget
+        if h % factor or w % factor or (hi is not None and h * w > hi) or (lo is not None and h * w < lo):
+            # livecc_utils' _spatial_resize_video (video_process_patch.py:133-153): smart_resize target, anti-aliased bicubic
+            from .utils.frames import smart_resize
+            h2, w2 = smart_resize(h, w, factor, lo if lo is not None else factor * factor, hi if hi is not None else max(h * w, factor * factor))
+            frames_thwc = _abi.frames_resize_bicubic(frames_thwc.contiguous(), h2, w2)
+            self.launches += 2
         self.launches += 1
         return _abi.frames_to_patches(frames_thwc, patch=g.patch_size, temporal_patch=g.temporal_patch_size, merge=g.spatial_merge_size)
 

@@ -265,6 +265,14 @@ def make_frame_ingest():
         out[name + "__frames_thwc"] = fr.permute(0, 2, 3, 1).contiguous().numpy()
         out[name + "__pixel_values"] = r["pixel_values_videos"].numpy()
         out[name + "__grid"] = r["video_grid_thw"].numpy()
+    # spatial resize exactly as livecc_utils' _spatial_resize_video calls it (video_process_patch.py:147-152), on uint8 TCHW clips
+    from torchvision.transforms import InterpolationMode
+    from torchvision.transforms import functional as TF
+    for name, (h, w, h2, w2, seed) in {"down": (90, 160, 56, 112, 11), "mixed": (37, 53, 28, 56, 12), "up": (50, 50, 84, 84, 13)}.items():
+        clip = synthetic.frames(seed, h, w)                                # uint8 [2, 3, h, w]
+        res = TF.resize(clip, [h2, w2], interpolation=InterpolationMode.BICUBIC, antialias=True)
+        out["resize_" + name + "__in_thwc"] = clip.permute(0, 2, 3, 1).contiguous().numpy()
+        out["resize_" + name + "__out_thwc"] = res.permute(0, 2, 3, 1).contiguous().numpy()
     fr = synthetic.frames(5, 448, 448)
     r = vp(videos=[fr], return_tensors="pt", do_resize=False)
     out["full__sha256"] = np.frombuffer(hashlib.sha256(r["pixel_values_videos"].numpy().tobytes()).digest(), dtype=np.uint8)

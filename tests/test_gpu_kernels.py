@@ -575,3 +575,26 @@ def test_vit_attn_matches_flash_attn_varlen(abi, cu):
     max_len = max(b - a for a, b in zip(cu[:-1], cu[1:]))
     ref = flash_attn_varlen_func(qkv[:, 0].contiguous(), qkv[:, 1].contiguous(), qkv[:, 2].contiguous(), cu_t, cu_t, max_len, max_len)
     torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), **ATT_TOL)
+
+
+@pytest.mark.gpu
+def test_frames_resize_bicubic(abi, golden_dir):
+    """Kernel == oracle bit for bit (same tap tables, same fp32 accumulation order); == torchvision within 1 LSB."""
+    from oracle import frames as o_frames
+    from streaming_vlm_b200 import synthetic
+    z = np.load(os.path.join(golden_dir, "frame_ingest.npz"))
+    for name in ("down", "mixed", "up"):
+        clip, want = torch.from_numpy(z[f"resize_{name}__in_thwc"]), torch.from_numpy(z[f"resize_{name}__out_thwc"])
+        got = abi.frames_resize_bicubic(clip.to(DEV), want.shape[1], want.shape[2]).cpu()
+        assert torch.equal(got, o_frames.resize_bicubic_aa(clip, want.shape[1], want.shape[2])), name
+        d = (got.int() - want.int()).abs()
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3
+    # a 720p clip to the size smart_resize picks, then straight into the patchifier
+    clip = synthetic.frames(9, 360, 640).permute(0, 2, 3, 1).contiguous()
+    from streaming_vlm_b200.utils.frames import smart_resize
+    h2, w2 = smart_resize(360, 640, 28, 128 * 28 * 28, 256 * 28 * 28)
+    small = abi.frames_resize_bicubic(clip.to(DEV), h2, w2)
+    assert torch.equal(small.cpu(), o_frames.resize_bicubic_aa(clip, h2, w2))
+    rows, grid = abi.frames_to_patches(small)
+    want_rows, want_grid = o_frames.frames_to_patches(small.cpu())
+    assert grid == want_grid and torch.equal(bits(rows.cpu()), bits(want_rows.to(torch.bfloat16)))

@@ -158,3 +158,27 @@ def test_qwen2_vl_tower_oracle_equals_hf_module():
     got = o_vit.vision_forward(px, [grid], w, geo.as_dict())
     assert got.shape == want.shape == (grid[0] * grid[1] * grid[2] // 4, 256)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_spatial_resize_oracle_vs_torchvision(golden_dir):
+    """oracle/frames.py::resize_bicubic_aa against torchvision's `resize(BICUBIC, antialias=True)` on uint8 clips (fixtures):
+    at most 1 LSB apart, on at most 0.1 % of the values (fp32 accumulation order at rounding boundaries); the product's tap
+    builder equals the oracle's bit for bit; `smart_resize` equals the copy that ships in transformers."""
+    from oracle import frames as o_frames
+    from streaming_vlm_b200.utils import frames as p_frames
+    z = np.load(os.path.join(golden_dir, "frame_ingest.npz"))
+    for name in ("down", "mixed", "up"):
+        clip, want = torch.from_numpy(z[f"resize_{name}__in_thwc"]), torch.from_numpy(z[f"resize_{name}__out_thwc"])
+        got = o_frames.resize_bicubic_aa(clip, want.shape[1], want.shape[2])
+        d = (got.int() - want.int()).abs()
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3, (name, int(d.max()), float((d > 0).float().mean()))
+    for n_in, n_out in [(160, 112), (90, 56), (100, 140), (53, 56), (448, 448), (1280, 700), (37, 28)]:
+        a, b = o_frames.aa_bicubic_taps(n_in, n_out), p_frames.aa_bicubic_taps(n_in, n_out)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.int32), b[2].view(np.int32))
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import smart_resize as hf_smart_resize
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        h, w = int(rng.integers(28, 2200)), int(rng.integers(28, 3900))
+        mn, mx = int(rng.choice([56 * 56, 128 * 28 * 28])), int(rng.choice([768 * 28 * 28, 602112, 16384 * 28 * 28]))
+        want = hf_smart_resize(h, w, 28, mn, mx)
+        assert o_frames.smart_resize(h, w, 28, mn, mx) == want and p_frames.smart_resize(h, w, 28, mn, mx) == want
