@@ -94,10 +94,17 @@ class StreamingEngine:
                  text_round=DEFAULT_TEXT_ROUND, text_sink=DEFAULT_TEXT_SINK, text_sliding_window=DEFAULT_TEXT_SLIDING_WINDOW,
                  max_new_tokens=MAX_TOKEN_PER_DURATION, suppress=None, assistant_start_bias=3, assistant_end_bias=2,
                  use_graph=True, decode_splits=None, prefill_splits=None, share_weights_from=None, pos_mode="shrink",
-                 max_position=None):
+                 max_position=None, tp_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         _abi.lib()
+        # head-sharded tensor parallelism (parallel.shard_llm_weights): `geo` and `weights` are this rank's shard, `tp_group` the
+        # NCCL group whose all-reduce sums the o_proj / down_proj partial products
+        self.tp_group = tp_group
+        if tp_group is not None:
+            # Replaying CUDA graphs that contain the NCCL all-reduces hung on this pool (both ranks stuck in the first replay, with
+            # or without the side-stream prefetch); the tensor-parallel mode therefore runs its steps eagerly.
+            use_graph = False
         self.geo, self.device = geo, torch.device(device)
         self.window_size, self.text_round = window_size, text_round
         self.text_sink, self.text_sliding_window = text_sink, text_sliding_window
@@ -144,6 +151,7 @@ class StreamingEngine:
         self._prefetch = os.environ.get("SVLM_DECODE_PREFETCH", "1") != "0"
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
+        self._dec_part = torch.zeros(g.hidden, dtype=torch.bfloat16, device=dev)
         self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
         self._pf_ids = torch.zeros(1024, dtype=torch.int64, device=dev)
         self.suppress_u8 = None if self.suppress is None else self.suppress.to(torch.uint8).contiguous()
@@ -208,6 +216,13 @@ class StreamingEngine:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             marks.append((name, e, time.perf_counter()))
+
+    def _reduce(self, t):
+        """Sum of the row-parallel partial products over the tensor-parallel group (identity without one)."""
+        if self.tp_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.tp_group)
+        return t
 
     def _rmsnorm(self, x, w, eps=1e-6):
         out = torch.empty_like(x)
@@ -316,9 +331,9 @@ class StreamingEngine:
         if taps is not None:
             taps.setdefault("attn_out", []).append(o.view(t, -1))
             taps.setdefault("q_rot", []).append(q_rot)
-        x, h = self._add_norm(x, F.linear(o.view(t, -1), L["wo"]), L["ln2"], g.rms_eps)
+        x, h = self._add_norm(x, self._reduce(F.linear(o.view(t, -1), L["wo"])), L["ln2"], g.rms_eps)
         gu = F.linear(h, L["wgu"])
-        return x, F.linear(self._swiglu(gu, g.mlp), L["wd"])
+        return x, self._reduce(F.linear(self._swiglu(gu, g.mlp), L["wd"]))
 
     def _logits(self, x_last, pending_last=None):
         _, h = self._add_norm(x_last, pending_last, self.norm, self.geo.rms_eps)
@@ -409,9 +424,17 @@ class StreamingEngine:
                              self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev)
             if self._prefetch:
                 main.wait_stream(self._side)
-            _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
-            _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
-            _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
+            if self.tp_group is None:
+                _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
+                _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
+                _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
+            else:       # row-parallel projections: partial product -> all-reduce -> residual add
+                part = self._dec_part
+                _abi.gemv_bf16(L["wo"], o.view(-1), part, 0)
+                x.add_(self._reduce(part))
+                _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
+                _abi.gemv_bf16(L["wd"], act, part, 0)
+                x.add_(self._reduce(part))
         self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0) + ((2 if self._prefetch_gu_bytes else 1) if self._prefetch else 0))
         _abi.lm_head_argmax(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
                             self.kv_len_dev, self.kv_after_dev, c.next_pos)
