@@ -18,7 +18,7 @@ from streaming_vlm_b200.config import QWEN25VL_32B, TINY
 from streaming_vlm_b200.engine import StreamingEngine
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
-use_graph = False       # see StreamingEngine.__init__: graph replay of the NCCL all-reduces hangs on this pool
+use_graph = True        # the engine itself falls back to eager steps under TP unless SVLM_TP_GRAPH=1 (see StreamingEngine.__init__)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)

@@ -103,8 +103,9 @@ class StreamingEngine:
         self.tp_group = tp_group
         if tp_group is not None:
             # Replaying CUDA graphs that contain the NCCL all-reduces hung on this pool (both ranks stuck in the first replay, with
-            # or without the side-stream prefetch); the tensor-parallel mode therefore runs its steps eagerly.
-            use_graph = False
+            # or without the side-stream prefetch, with or without NCCL_GRAPH_MIXING_SUPPORT=0); the tensor-parallel mode
+            # therefore runs its steps eagerly unless SVLM_TP_GRAPH=1 asks for the experiment.
+            use_graph = use_graph and os.environ.get("SVLM_TP_GRAPH", "0") == "1"
         self.geo, self.device = geo, torch.device(device)
         self.window_size, self.text_round = window_size, text_round
         self.text_sink, self.text_sliding_window = text_sink, text_sliding_window
