@@ -364,6 +364,11 @@ def register_torch_ops():
     L.define("vit_attn(Tensor(a!) qkv, Tensor cos, Tensor sin, Tensor cu_seqlens, float scale) -> Tensor")
     L.define("gemm_bf16(Tensor a, Tensor w, Tensor? bias, int act, Tensor? out_rows) -> Tensor")
     L.define("rmsnorm(Tensor x, Tensor weight, float eps) -> Tensor")
+    L.define("add_rmsnorm(Tensor a, Tensor b, Tensor weight, float eps) -> (Tensor, Tensor)")
+    L.define("swiglu(Tensor gate_up) -> Tensor")
+    L.define("gemv(Tensor w, Tensor x, int mode, Tensor? norm_weight, float eps, Tensor? bias, Tensor? residual) -> Tensor")
+    L.define("frames_to_patches(Tensor frames_thwc, int patch, int temporal_patch, int merge) -> Tensor")
+    L.define("frames_resize_bicubic(Tensor frames_thwc, int out_h, int out_w) -> Tensor")
 
     def _kv_compact_rope(arena, src_buffer, runs, pos, cos_table, sin_table, section):
         kv_compact_rope(ArenaView(arena), src_buffer, [tuple(runs[i:i + 3]) for i in range(0, len(runs), 3)], pos, cos_table,
@@ -403,8 +408,28 @@ def register_torch_ops():
         rmsnorm(x, weight, out, eps)
         return out
 
+    def _add_rmsnorm(a, b, weight, eps):
+        s_, h = torch.empty_like(a), torch.empty_like(a)
+        add_rmsnorm(a, b, weight, s_, h, eps)
+        return s_, h
+
+    def _swiglu(gate_up):
+        out = torch.empty(gate_up.shape[0], gate_up.shape[1] // 2, dtype=gate_up.dtype, device=gate_up.device)
+        swiglu(gate_up, out)
+        return out
+
+    def _gemv(w, x, mode, norm_weight, eps, bias, residual):
+        n = w.shape[0] // 2 if mode == 2 else w.shape[0]
+        y = torch.empty(n, dtype=x.dtype, device=x.device)
+        gemv_bf16(w, x, y, mode, norm_weight, eps, bias, residual)
+        return y
+
+    def _frames_to_patches(frames_thwc, patch, temporal_patch, merge):
+        return frames_to_patches(frames_thwc, patch=patch, temporal_patch=temporal_patch, merge=merge)[0]
+
     for name, fn in [("kv_compact_rope", _kv_compact_rope), ("mrope_positions", _mrope_positions),
                      ("qkv_rope_append", _qkv_rope_append), ("attn_causal", _attn_causal), ("vit_attn", _vit_attn),
-                     ("gemm_bf16", _gemm), ("rmsnorm", _rmsnorm)]:
+                     ("gemm_bf16", _gemm), ("rmsnorm", _rmsnorm), ("add_rmsnorm", _add_rmsnorm), ("swiglu", _swiglu), ("gemv", _gemv),
+                     ("frames_to_patches", _frames_to_patches), ("frames_resize_bicubic", frames_resize_bicubic)]:
         L.impl(name, fn, "CUDA")
     register_torch_ops._lib = L     # keep the Library object alive

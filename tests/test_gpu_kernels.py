@@ -598,3 +598,32 @@ def test_frames_resize_bicubic(abi, golden_dir):
     rows, grid = abi.frames_to_patches(small)
     want_rows, want_grid = o_frames.frames_to_patches(small.cpu())
     assert grid == want_grid and torch.equal(bits(rows.cpu()), bits(want_rows.to(torch.bfloat16)))
+
+
+@pytest.mark.gpu
+def test_torch_custom_ops_layer(abi):
+    """The thin `torch.ops.svlm.*` layer (CUDA key only) returns what the ctypes wrappers return."""
+    abi.register_torch_ops()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(5, 512, generator=g).to(torch.bfloat16).to(DEV)
+    b = torch.randn(5, 512, generator=g).to(torch.bfloat16).to(DEV)
+    wn = torch.rand(512, generator=g).to(torch.bfloat16).to(DEV)
+    s_, h = torch.ops.svlm.add_rmsnorm(a, b, wn, 1e-6)
+    s2, h2 = torch.empty_like(a), torch.empty_like(a)
+    abi.add_rmsnorm(a, b, wn, s2, h2, 1e-6)
+    assert torch.equal(bits(s_), bits(s2)) and torch.equal(bits(h), bits(h2))
+    gu = torch.randn(5, 1024, generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.empty(5, 512, dtype=torch.bfloat16, device=DEV)
+    abi.swiglu(gu, out)
+    assert torch.equal(bits(torch.ops.svlm.swiglu(gu)), bits(out))
+    w = (torch.randn(256, 512, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+    x = torch.randn(512, generator=g).to(torch.bfloat16).to(DEV)
+    y = torch.empty(256, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_bf16(w, x, y, 0, wn, 1e-6)
+    assert torch.equal(bits(torch.ops.svlm.gemv(w, x, 0, wn, 1e-6, None, None)), bits(y))
+    assert torch.ops.svlm.gemv(w, x, 2, wn, 1e-6, None, None).shape == (128,)
+    fr = torch.randint(0, 256, (2, 56, 84, 3), dtype=torch.uint8, generator=g).to(DEV)
+    assert torch.equal(bits(torch.ops.svlm.frames_to_patches(fr, 14, 2, 2)), bits(abi.frames_to_patches(fr)[0]))
+    assert torch.equal(torch.ops.svlm.frames_resize_bicubic(fr, 28, 56), abi.frames_resize_bicubic(fr, 28, 56))
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.svlm.swiglu(gu.cpu())              # no CPU kernel is registered: there is no fallback
