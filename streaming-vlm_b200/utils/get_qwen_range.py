@@ -59,24 +59,28 @@ def find_segments(ids: np.ndarray, label: str, contain_lf: bool = True):
         hit &= ids[j: n - m + 1 + j] == pat[j]
     starts = np.flatnonzero(hit)
     ends = np.flatnonzero(ids == end_tok)
+    if starts.size == 0 or ends.size == 0:
+        return []
     lf = TOKEN_IDS["\n"]
-    out = []
-    cur = 0                       # scan cursor
-    while True:
-        si = int(np.searchsorted(starts, cur, side="left"))
-        if si >= starts.shape[0]:
-            break
-        s = int(starts[si])
-        ei = int(np.searchsorted(ends, s + m, side="left"))
-        if ei >= ends.shape[0]:
-            break                 # no terminator: the scan ends (reference :80-81)
-        e = int(ends[ei])
-        if contain_lf and e + 1 < n and ids[e + 1] == lf:
-            out.append((s, e + 1))
-        else:
-            out.append((s, e))
-        cur = e + 1
-    return out
+    # terminator of every candidate start, all at once; a start without one ends the scan (reference :80-81)
+    e_idx = np.searchsorted(ends, starts + m, side="left")
+    live = e_idx < ends.shape[0]
+    starts, e_idx = starts[live], e_idx[live]
+    if starts.size == 0:
+        return []
+    e = ends[e_idx]
+    if starts.size > 1 and not bool(np.all(starts[1:] > e[:-1])):
+        # a candidate begins inside the previous segment (adversarial input): fall back to the sequential greedy scan
+        keep, cur = [], 0
+        for k in range(starts.shape[0]):
+            if starts[k] >= cur:
+                keep.append(k)
+                cur = int(e[k]) + 1
+        starts, e = starts[keep], e[keep]
+    if contain_lf:
+        nxt = np.minimum(e + 1, n - 1)
+        e = np.where((e + 1 < n) & (ids[nxt] == lf), e + 1, e)
+    return list(zip(starts.tolist(), e.tolist()))
 
 
 def get_qwen_range(input_ids, label: str, index: int, contain_lf: bool = True):
