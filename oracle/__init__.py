@@ -20,8 +20,9 @@ flash-attn 2.8.3 in the reference, which has no CPU path: here the oracle is the
 softmax(QK^T)V definition, and the CUDA kernels are additionally compared with flash-attn
 itself on the GPU box (`tests/test_gpu_kernels.py::test_attn_causal_matches_flash_attn`,
 `::test_vit_attn_matches_flash_attn_varlen`).  The `pos_mode="append"` arithmetic
-(`model_forward.py:112-153`) is restated (it lives inside a model method); its
-`get_rope_index` component is the pinned one.
+(`model_forward.py:112-153`) is pinned too: the reference's `model_forward` is exec'd with
+a stub model and the `position_ids` it hands to the language model are the fixture
+(`tests/golden/append_positions.json`).
 
 Module map (reference file:line each one follows is cited in the module docstrings):
     tokens.py      get_qwen_range                      utils/get_qwen_range.py:15-86

@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from .attention import attention
 from .cache import ListCache
 from .eviction import process_past_kv
-from .positions import apply_mrope, default_inv_freq, get_rope_index, rotary_cos_sin
+from .positions import append_mode_positions, apply_mrope, default_inv_freq, get_rope_index, rotary_cos_sin
 from .tokens import IM_END, LF, VIDEO_PAD
 from .vit import rmsnorm, vision_forward
 
@@ -86,14 +86,7 @@ def model_forward(new_ids, full_ids, grids, cache, w, geo, pixels=None, pixel_gr
         if taps is not None:
             taps["video_embeds"] = vid
     if pos_mode == "append":
-        if cache.get_seq_length() == 0:                                            # prefill (:114-127)
-            pos, _ = get_rope_index(new_ids, pixel_grid, geo["spatial_merge_size"], geo["tokens_per_second"])
-        elif len(new_ids) != 1:                                                    # chunk prefill (:128-137)
-            pos, _ = get_rope_index(new_ids, pixel_grid, geo["spatial_merge_size"], geo["tokens_per_second"])
-            pos = pos + float(state["last_cache_position"] + 1)
-        else:                                                                      # decode (:138-151)
-            pos = torch.full((3, 1, 1), float(state["last_cache_position"] + 1))
-        state["last_cache_position"] = int(pos[0, 0, -1])                          # (:153)
+        pos = append_mode_positions(new_ids, pixel_grid, cache.get_seq_length(), state, geo["spatial_merge_size"], geo["tokens_per_second"])
     else:
         pos, _ = get_rope_index(full_ids, grids, geo["spatial_merge_size"], geo["tokens_per_second"])
         cache.update_position_ids(pos)

@@ -107,3 +107,19 @@ def apply_mrope(q, k, cos, sin, mrope_section=(16, 24, 24)):
     q_rot = (q * qc) + (rotate_half(q) * qs)
     k_rot = (k * c) + (rotate_half(k) * s)
     return q_rot, k_rot
+
+
+def append_mode_positions(new_ids, chunk_grids, cache_len: int, state: dict, spatial_merge_size=2, tokens_per_second=2):
+    """`pos_mode="append"` (qwen2_5/model_forward.py:112-153): positions of the NEW tokens only.  Empty cache: plain
+    `get_rope_index` over the ids (:114-127); chunk prefill: `get_rope_index` over the new ids with this chunk's grids, shifted by
+    `last_cache_position + 1` (:128-137); single token: `last_cache_position + 1` on all three axes (:138-151).  Updates
+    `state["last_cache_position"]` with the time-axis position of the last token (:153).  Returns float32 [3, 1, T]."""
+    if cache_len == 0:
+        pos, _ = get_rope_index(new_ids, chunk_grids, spatial_merge_size, tokens_per_second)
+    elif len(new_ids) != 1:
+        pos, _ = get_rope_index(new_ids, chunk_grids, spatial_merge_size, tokens_per_second)
+        pos = pos + float(state["last_cache_position"] + 1)
+    else:
+        pos = torch.full((3, 1, 1), float(state["last_cache_position"] + 1))
+    state["last_cache_position"] = int(pos[0, 0, -1])
+    return pos

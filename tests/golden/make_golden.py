@@ -250,6 +250,59 @@ def main():
                         q_rot=qe.view(torch.int16).numpy(), k_rot=ke.view(torch.int16).numpy())
     print("mrope", qe.shape, ke.shape)
     make_frame_ingest()
+    make_append_positions(ns2["get_rope_index"])
+
+
+def make_append_positions(ref_get_rope_index):
+    """`pos_mode="append"`: the reference's `model_forward` (qwen2_5/model_forward.py:30-176) itself, exec'd from its source and
+    called with a stub `self` whose `get_rope_index` is the reference's and whose `language_model` records the `position_ids`
+    it is handed.  `inputs_embeds` is passed in, so no weights are involved: what is recorded is exactly the position policy
+    (:112-153) over a stream of chunk prefills (new ids only, as HF's generate passes them) and single-token decode steps."""
+    import typing
+    ns = {"torch": torch, "Optional": typing.Optional, "List": typing.List, "Tuple": typing.Tuple, "Union": typing.Union,
+          "StreamingArgs": object, "Qwen2_5_VLModelOutputWithPast": lambda **kw: types.SimpleNamespace(**kw)}
+    _exec_functions(f"{REF}/streaming_vlm/inference/qwen2_5/model_forward.py", ["get_1d_rope_index", "model_forward"], ns)
+    seen = []
+
+    class Self:
+        rope_deltas = None
+        config = types.SimpleNamespace(output_attentions=False, output_hidden_states=False, use_return_dict=True,
+                                       vision_config=types.SimpleNamespace(spatial_merge_size=2, tokens_per_second=2),
+                                       image_token_id=151655, video_token_id=151656, vision_start_token_id=151652)
+
+        def get_rope_index(self, *a, **k):
+            return ref_get_rope_index(self, *a, **k)
+
+        def language_model(self, **kw):
+            seen.append(kw["position_ids"].clone())
+            return types.SimpleNamespace(last_hidden_state=None, past_key_values=kw["past_key_values"], hidden_states=None, attentions=None)
+
+    me = Self()
+    args = types.SimpleNamespace(pos_mode="append", all_text=False, input_ids=None, video_grid_thw=None, second_per_grid_ts=None,
+                                 last_cache_position=-1)
+    rng = np.random.RandomState(7)
+    cached, chunks = 0, []
+    for i in range(10):
+        n_vis = [16, 64, 16, 256][i % 4]
+        side = int(round((n_vis * 4) ** 0.5))
+        grid = torch.tensor([[1, side, side]])
+        new = ([151645] if i else []) + synthetic.round_prompt(i, n_vis, 6, 8, 3)
+        n_dec = int(rng.randint(1, 7))
+        rec = {"new_ids": new, "grid": grid[0].tolist(), "n_decode": n_dec, "pos": []}
+        for step in range(1 + n_dec):
+            ids = torch.tensor([new]) if step == 0 else torch.tensor([[1000 + step]])
+            t = ids.shape[1]
+            cache = types.SimpleNamespace(get_seq_length=lambda c=cached: c)
+            ns["model_forward"](me, input_ids=ids, attention_mask=torch.ones(1, cached + t, dtype=torch.long), past_key_values=cache,
+                                inputs_embeds=torch.zeros(1, t, 8), video_grid_thw=grid if step == 0 else None,
+                                cache_position=torch.arange(cached, cached + t), streaming_args=args)
+            rec["pos"].append(seen[-1][:, 0, :].to(torch.int64).tolist())
+            cached += t
+        rec["last_cache_position"] = int(args.last_cache_position)
+        chunks.append(rec)
+        cached = max(cached - int(rng.randint(0, 40)), 1)          # an eviction in between: irrelevant to append-mode positions
+    json.dump({"chunks": chunks}, open(os.path.join(HERE, "append_positions.json"), "w"))
+    print("append positions", len(chunks), "chunks, last position", chunks[-1]["last_cache_position"])
 
 
 def make_frame_ingest():

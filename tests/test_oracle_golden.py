@@ -182,3 +182,19 @@ def test_spatial_resize_oracle_vs_torchvision(golden_dir):
         mn, mx = int(rng.choice([56 * 56, 128 * 28 * 28])), int(rng.choice([768 * 28 * 28, 602112, 16384 * 28 * 28]))
         want = hf_smart_resize(h, w, 28, mn, mx)
         assert o_frames.smart_resize(h, w, 28, mn, mx) == want and p_frames.smart_resize(h, w, 28, mn, mx) == want
+
+
+def test_append_mode_positions_equal_reference_model_forward(golden_dir):
+    """`pos_mode="append"`: oracle/positions.py::append_mode_positions against the positions the reference's own `model_forward`
+    (exec'd with a stub model, tests/golden/make_golden.py::make_append_positions) handed to the language model, over ten chunk
+    prefills with different grids and the decode steps after them."""
+    z = json.load(open(os.path.join(golden_dir, "append_positions.json")))
+    state = {"last_cache_position": -1}
+    cached = 0
+    for i, ch in enumerate(z["chunks"]):
+        for step, want in enumerate(ch["pos"]):
+            new = ch["new_ids"] if step == 0 else [1000 + step]
+            got = positions.append_mode_positions(new, [tuple(ch["grid"])], cached, state)
+            assert got[:, 0, :].to(torch.int64).tolist() == want, f"chunk {i} step {step}"
+            cached += len(new)
+        assert state["last_cache_position"] == ch["last_cache_position"], f"chunk {i}"
