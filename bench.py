@@ -492,6 +492,8 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="streams per GPU of the extra multi-stream leg (BASELINE configs[3]); 1 = skip")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around timed region 1 (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    if args.impl != "reference":
+        args.warmup = max(args.warmup, 3)      # timing rule: at least 3 untimed warm-up steps (CUDA-graph capture happens there)
     if args.impl == "reference":
         run_reference(args)
     else:
