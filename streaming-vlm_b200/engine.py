@@ -148,7 +148,7 @@ class StreamingEngine:
         # side stream of the decode step: L2 prefetch of the o_proj weights and the head of the gate/up weights while the
         # (latency-bound, HBM-idle) attention runs; SVLM_DECODE_PREFETCH_MB = MiB of gate/up to pull (0 disables the branch)
         self._side = torch.cuda.Stream(device=dev)
-        self._prefetch_gu_bytes = int(float(os.environ.get("SVLM_DECODE_PREFETCH_MB", "32")) * (1 << 20))
+        self._prefetch_gu_bytes = int(float(os.environ.get("SVLM_DECODE_PREFETCH_MB", "16")) * (1 << 20))
         self._prefetch = os.environ.get("SVLM_DECODE_PREFETCH", "1") != "0"
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
