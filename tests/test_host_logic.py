@@ -71,3 +71,28 @@ def test_prune_interval():
     new_ids, c = host.prune_id_and_kv_cache(ids, c, 3, 6)
     assert new_ids.flatten().tolist() == [0, 1, 2] + list(range(7, 20))
     assert c.gather == [0, 1, 2] + list(range(7, 18))
+
+
+# ------------------------------------------------------------------------------------------------ property test of the range finder
+def test_find_segments_equals_oracle_on_random_token_soups():
+    """The vectorised range finder of the product against the oracle's sequential restatement of `get_qwen_range` on random
+    sequences over the structural tokens (nested, unterminated and overlapping patterns included), every label, both
+    `contain_lf` settings."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import tokens as o_tok
+    from streaming_vlm_b200.utils.get_qwen_range import TOKEN_IDS, find_segments
+    alphabet = [TOKEN_IDS["<|im_start|>"], TOKEN_IDS["<|im_end|>"], TOKEN_IDS["user"], TOKEN_IDS["assistant"], TOKEN_IDS["Time"],
+                TOKEN_IDS["\n"], TOKEN_IDS["<|vision_start|>"], TOKEN_IDS["<|vision_end|>"], TOKEN_IDS["<|video_pad|>"],
+                *TOKEN_IDS["previous text"], 1000, 1001]
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.sampled_from(alphabet), min_size=0, max_size=60))
+    def check(ids):
+        arr = np.asarray(ids, dtype=np.int64)
+        for label in ("user", "previous text", "user_text", "assistant", "vision"):
+            for lf in (True, False):
+                want = [tuple(x) for x in o_tok.all_ranges(ids, label, lf)]
+                got = find_segments(arr, label, lf)
+                assert got == want, (label, lf, ids)
+
+    check()
