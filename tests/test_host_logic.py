@@ -96,3 +96,64 @@ def test_find_segments_equals_oracle_on_random_token_soups():
                 assert got == want, (label, lf, ids)
 
     check()
+
+
+def test_planner_equals_oracle_on_random_policies():
+    """Product planner (`plan_past_kv`, numpy) against the oracle's `plan_eviction` (pinned on five policies) over 40 RANDOM
+    policies -- window, text rounds, sink and sliding-window sizes, turn lengths, early <|im_end|> -- 24 rounds each: pruned ids
+    and gather maps must agree everywhere the oracle accepts the configuration, and both must refuse where it does not."""
+    import copy
+    from oracle import eviction as o_ev
+    from streaming_vlm_b200 import synthetic
+    from streaming_vlm_b200.inference.inference import plan_past_kv
+    rng = np.random.RandomState(2024)
+    compared = refused = 0
+    for _ in range(40):
+        window, text_round = int(rng.randint(1, 7)), int(rng.randint(1, 7))
+        sink = None if rng.rand() < 0.2 else int(rng.randint(2, 40))
+        slide = None if rng.rand() < 0.2 else int(rng.randint(2, 40))
+        n_vis, n_prev, seed = int(rng.choice([4, 16])), int(rng.randint(2, 30)), int(rng.randint(0, 1000))
+        hist_o, clips_o, px_o = [], [], []
+        hist_p, clips_p, px_p = [], [], []
+        prev = None
+        for i in range(24):
+            if prev is not None:
+                cache_len = len(prev) - 1
+                try:
+                    want_ids, gather = o_ev.plan_eviction(list(prev), i, text_round, window, hist_o, 3, 2, clips_o, px_o, sink, slide)
+                    ok = True
+                except (AssertionError, IndexError):
+                    ok = False
+                if not ok:
+                    with pytest.raises((AssertionError, IndexError)):
+                        plan_past_kv(np.asarray(prev), i, text_round, window, hist_p, 3, 2, clips_p, px_p, sink, slide)
+                    refused += 1
+                    break
+                plan = plan_past_kv(np.asarray(prev), i, text_round, window, hist_p, 3, 2, clips_p, px_p, sink, slide)
+                assert plan.ids.tolist() == want_ids, (window, text_round, sink, slide, i)
+                got = [s_ + k for s_, _, l in plan.runs(cache_len) for k in range(l)]
+                assert got == [g for g in gather if g < cache_len], (window, text_round, sink, slide, i)
+                assert hist_p == hist_o and len(clips_p) == len(clips_o)
+                prev = want_ids
+                compared += 1
+            for clips, px, hist in ((clips_o, px_o, hist_o), (clips_p, px_p, hist_p)):
+                clips.append(None)
+                px.append(None)
+                if i == 0:
+                    hist[:] = [{"role": "previous text", "content": "p" * 10},
+                               {"role": "user", "content": [{"type": "text", "text": "T"}, {"type": "video"}, {"type": "text", "text": "q"}]}]
+                else:
+                    hist.append({"role": "user", "content": [{"type": "text", "text": "T"}, {"type": "video"}]})
+            prompt = synthetic.round_prompt(i, n_vis, n_prev, 8, seed)
+            ids = prompt if prev is None else list(prev) + (prompt if prev[-1] != 198 else prompt[1:])
+            gen = [int(x) for x in rng.randint(1000, 100000, size=int(rng.randint(1, 13)))]
+            gen = [g if g not in (872, 77091, 1462, 198, 19702, 1467) else 1000 for g in gen]
+            if rng.rand() < 0.3:
+                gen[-1] = 151645
+            seq = ids + gen
+            if seq[-1] != 151645:
+                seq = seq + [151645]
+            prev = seq
+            for hist in (hist_o, hist_p):
+                hist.append({"role": "assistant", "content": "x" * 8 + " ..."})
+    assert compared > 500, (compared, refused)
