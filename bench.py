@@ -10,11 +10,19 @@ decoded commentary tokens, on a random-init Qwen2.5-VL-7B-architecture model in 
 into the steady state of a long stream (round 200 of the default 16/16/512/512 policy) by replaying the
 host-side bookkeeping and filling the arena; nothing inside the timed region is skipped.
 
+The timed call is the REFERENCE-FACING one: a stock transformers Qwen2_5_VLForConditionalGeneration (7B architecture, random
+init) patched with `convert_qwen2_5_to_streaming`, driven by the reference's own loop body (`inference/inference.py:319,
+397-416, 440-463`): `process_past_kv(...)` -> `model.generate(**inputs, past_key_values=..., streaming_args=...,
+do_sample=True, temperature=0.9, repetition_penalty=1.05, max_new_tokens=20)`.  `value`: frames resident in HBM; `e2e`: uint8
+frames in pinned host memory, ids / tokens through the host as the loop does.  `engine_api`: the same chunks through
+`StreamingEngine.step` directly (greedy), for comparison.
+
 N > 1 (torchrun): every rank runs its own independent stream (no data-path collective; the reference's
 one-process-per-GPU sharding, eval/livesports3kcc/distributed_generate_streaming.py:53-62) -> weak scaling.
 
 `--impl reference`: the reference's path restated on the CPU (the oracle port; the reference itself cannot be
-imported here) on the host cores, per step a bounded, layer-count-scaled sample of the same chunk.
+imported here) on the host cores: full-depth steady-state chunks (28 layers, 32 ViT blocks, all decode forwards),
+nothing extrapolated (SVLM_CPU_SAMPLE=scaled restores the layer-count-scaled sample for small hosts).
 """
 import argparse
 import copy
@@ -85,17 +93,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_chunk_sample(n_threads, llm_layers=4, vit_blocks=8, decode_tokens=2, steps=1, warmup=0, budget_s=240.0):
-    """The reference path (oracle port) on the host cores: steady-state chunk, layer-count-scaled sample.
-    Returns (frames/s estimate, description, per-step chunk-time list)."""
+def cpu_chunk_sample(n_threads, steps=1, warmup=0, budget_s=240.0, scaled=None):
+    """The reference path (oracle port) on the host cores: steady-state chunks of the same workload.  Default: FULL depth (all 28
+    LLM layers, all 32 ViT blocks, every decode forward of the turn), nothing extrapolated.  `scaled` (SVLM_CPU_SAMPLE=scaled):
+    4/28 layers, 8/32 blocks, 2 decode forwards, scaled by layer count.  Returns (frames/s, description, per-step chunk seconds)."""
     from oracle.cache import ListCache
     from oracle.model import Session
     from streaming_vlm_b200 import synthetic
     from streaming_vlm_b200.config import QWEN25VL_7B as G7
+    if scaled is None:
+        scaled = os.environ.get("SVLM_CPU_SAMPLE", "full") == "scaled"
+    llm_layers, vit_blocks, decode_tokens = (4, 8, 2) if scaled else (G7.num_layers, G7.vit_depth, NEW_TOKENS - 1)
     torch.set_num_threads(n_threads)
     geo = G7.as_dict()
     geo["num_layers"], geo["vit_depth"] = llm_layers, vit_blocks
-    geo["fullatt_block_indexes"] = [vit_blocks - 1]            # 1 full-attention block in 8, as 4 in 32
+    if scaled:
+        geo["fullatt_block_indexes"] = [vit_blocks - 1]            # 1 full-attention block in 8, as 4 in 32
     w = synthetic.block_weights_cpu(G7, seed=0, layers=llm_layers, vit_blocks=vit_blocks)
     state = synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS)
     sess = Session(w, geo, max_new_tokens=1 + decode_tokens, suppress=synthetic.suppress_mask(G7.vocab))
@@ -112,17 +125,19 @@ def cpu_chunk_sample(n_threads, llm_layers=4, vit_blocks=8, decode_tokens=2, ste
     t_start = time.perf_counter()
     for s in range(warmup + steps):
         i = sess.i
-        # keep the stream in steady state: generated text of the sample chunk is padded to NEW_TOKENS below
         px, grid = synthetic.patchify(synthetic.frames(i), G7, dtype=torch.bfloat16)
         r = sess.step(synthetic.round_prompt(i), px, grid)
         tm = sess.timing[-1]
-        lscale = G7.num_layers / llm_layers
-        vit = (tm["vit_total"] - tm["vit_blocks"]) + tm["vit_blocks"] * (G7.vit_depth / vit_blocks)
-        prefill = tm["prefill_layers"] * lscale
-        dec_layers = tm["decode_layers"] / max(tm["n_decode_layers"], 1) * lscale
-        # non-layer parts of a forward (embedding, positions, final norm, lm_head): GEN minus the timed layer parts
-        other = max(tm["GEN"] - tm["vit_total"] - tm["prefill_layers"] - tm["decode_layers"], 0.0) / tm["n_forward"]
-        chunk = tm["PKV"] * lscale + vit + prefill + other + (NEW_TOKENS - 1) * (dec_layers + other)
+        if scaled:
+            lscale = G7.num_layers / llm_layers
+            vit = (tm["vit_total"] - tm["vit_blocks"]) + tm["vit_blocks"] * (G7.vit_depth / vit_blocks)
+            prefill = tm["prefill_layers"] * lscale
+            dec_layers = tm["decode_layers"] / max(tm["n_decode_layers"], 1) * lscale
+            # non-layer parts of a forward (embedding, positions, final norm, lm_head): GEN minus the timed layer parts
+            other = max(tm["GEN"] - tm["vit_total"] - tm["prefill_layers"] - tm["decode_layers"], 0.0) / tm["n_forward"]
+            chunk = tm["PKV"] * lscale + vit + prefill + other + (NEW_TOKENS - 1) * (dec_layers + other)
+        else:
+            chunk = tm["PKV"] + tm["GEN"]           # the reference's own sections (inference.py:312-329, 422-452), measured in full
         if s >= warmup:
             times.append(chunk)
         # pad this round's generated text to NEW_TOKENS so that the next round sees a steady-state sequence
@@ -137,9 +152,13 @@ def cpu_chunk_sample(n_threads, llm_layers=4, vit_blocks=8, decode_tokens=2, ste
         if time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
     chunk = statistics.median(times)
-    desc = (f"1 steady-state chunk (S~{n}): eviction + ViT + prefill + {decode_tokens} of {NEW_TOKENS - 1} decode forwards, timed on "
-            f"{llm_layers}/{G7.num_layers} LLM layers and {vit_blocks}/{G7.vit_depth} ViT blocks (1 full-attention) and scaled by layer "
-            f"count; embedding/merger/lm_head full size; {len(times)} timed step(s), median")
+    if scaled:
+        desc = (f"1 steady-state chunk (S~{n}): eviction + ViT + prefill + {decode_tokens} of {NEW_TOKENS - 1} decode forwards, timed on "
+                f"{llm_layers}/{G7.num_layers} LLM layers and {vit_blocks}/{G7.vit_depth} ViT blocks (1 full-attention) and scaled by layer "
+                f"count; embedding/merger/lm_head full size; {len(times)} timed step(s), median")
+    else:
+        desc = (f"{len(times)} full steady-state chunk(s) (S~{n}), median: eviction + ViT (32 blocks) + prefill (28 layers) + {decode_tokens} decode "
+                f"forwards, every layer executed, nothing extrapolated; PKV + GEN sections of the reference's loop")
     return FRAMES_PER_CHUNK / chunk, desc, times
 
 
@@ -149,20 +168,28 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     steps = max(1, args.steps)
-    value, desc, times = cpu_chunk_sample(cores, steps=steps, warmup=min(args.warmup, 1))
+    # ~7 s per full chunk on 16 cores: the whole --steps K --warmup W run must end within a few minutes
+    value, desc, times = cpu_chunk_sample(cores, steps=steps, warmup=min(args.warmup, 1), budget_s=200.0)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host_streams": 1,
+            "note": "ONE stream on all host cores, on rank 0, whatever --gpus says: N CPU streams would share the same cores, so "
+                    "this is also the host's aggregate rate; compare it with the N = 1 line only"}
     print(json.dumps(line), flush=True)
 
 
 def workload_config():
     return {"workload": "configs[1]: Qwen2.5-VL-7B-architecture random-init, single stream per GPU, 2 fps 448x448 synthetic video, "
                         "steady state of the sink512/text-window512/vision-window16 policy (round 200, S~5.8k), per-second "
-                        "commentary decode of 20 tokens, greedy",
+                        "commentary decode of 20 tokens",
+            "api": "reference loop body: process_past_kv + convert_qwen2_5_to_streaming(model).generate (value and e2e); "
+                   "engine_api = StreamingEngine.step",
+            "generation": "do_sample=True, temperature=0.9, repetition_penalty=1.05 (the reference's defaults, inference.py:41-42) for "
+                          "value / e2e; greedy (the parity mode) for engine_api and the CPU arm",
             "chunk": {"frames": FRAMES_PER_CHUNK, "vit_tokens": 1024, "llm_vision_tokens": 256, "new_tokens": NEW_TOKENS,
                       "input": "uint8 RGB frames [2,448,448,3]; normalise + patchify (svlm_frames_to_patches) inside the step"},
             "policy": {"window_size": 16, "text_round": 16, "text_sink": 512, "text_sliding_window": 512},
@@ -359,10 +386,157 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     return out
 
 
+def build_hf_model(geo, weights, dev):
+    """A stock transformers Qwen2_5_VLForConditionalGeneration of geometry `geo` whose parameters ARE the tensors of `weights`
+    (constructed on the meta device, then `load_state_dict(assign=True)`: no second copy, no init pass over 8 B parameters)."""
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    text = dict(hidden_size=geo.hidden, num_hidden_layers=geo.num_layers, num_attention_heads=geo.num_heads, num_key_value_heads=geo.num_kv_heads,
+                intermediate_size=geo.mlp, vocab_size=geo.vocab, rms_norm_eps=geo.rms_eps, tie_word_embeddings=False,
+                rope_parameters={"rope_type": "default", "rope_theta": geo.rope_theta, "mrope_section": list(geo.mrope_section)})
+    vis = dict(depth=geo.vit_depth, hidden_size=geo.vit_hidden, num_heads=geo.vit_heads, intermediate_size=geo.vit_mlp, out_hidden_size=geo.hidden,
+               patch_size=geo.patch_size, temporal_patch_size=geo.temporal_patch_size, spatial_merge_size=geo.spatial_merge_size,
+               window_size=geo.window_size, fullatt_block_indexes=list(geo.fullatt_block_indexes), tokens_per_second=geo.tokens_per_second)
+    cfg = Qwen2_5_VLConfig(text_config=text, vision_config=vis, tie_word_embeddings=False)
+    with torch.device("meta"):
+        model = Qwen2_5_VLForConditionalGeneration(cfg).to(torch.bfloat16)
+    missing, unexpected = model.load_state_dict(weights, assign=True, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f"synthetic weights do not cover the HF model: missing {missing[:4]}, unexpected {unexpected[:4]}")
+    return model.eval()
+
+
+class DropInSession:
+    """The reference's per-stream loop state and loop body (`inference/inference.py:297-303, 309-517`), product side: everything a
+    maintainer's unchanged `streaming_inference` does between reading two frames and appending the assistant turn."""
+
+    def __init__(self, model, geo, state, dev, sup, gen_kwargs):
+        from streaming_vlm_b200.inference.streaming_args import StreamingArgs
+        self.model, self.geo, self.dev, self.sup, self.gen_kwargs = model, geo, dev, sup, gen_kwargs
+        self.args = StreamingArgs(pos_mode="shrink")
+        self.past = model._svlm_engine.cache
+        self.prev = torch.tensor([state["prev_ids"]], dtype=torch.long, device=dev)
+        self.history, self.clips, self.pixels = state["history"], state["clips"], state["pixels"]
+        self.i = int(state["i"])
+        self.args.video_grid_thw = torch.tensor([list(g) for g in state["grids"]], dtype=torch.long, device=dev)
+        self.timing = []
+
+    def step(self, prompt_ids, frames_thwc):
+        from streaming_vlm_b200.inference.inference import process_past_kv
+        torch.ops.svlm  # noqa: B018  (custom ops registered by convert_qwen2_5_to_streaming)
+        i = self.i
+        t0 = time.perf_counter()
+        self.past, self.prev, self.clips, self.pixels = process_past_kv(
+            self.past, i, DEFAULT_POLICY["text_round"], DEFAULT_POLICY["window_size"], self.history, self.prev, 3, 2, self.clips, self.pixels,
+            DEFAULT_POLICY["text_sink"], DEFAULT_POLICY["text_sliding_window"])
+        t_pkv = time.perf_counter() - t0
+        self.clips.append(None)
+        self.history.append({"role": "user", "content": [{"type": "text", "text": "Time"}, {"type": "video"}]})
+        # the pixel half of `processor(text=..., videos=clip)` (inference.py:390-395): normalise + patchify on the GPU
+        px = torch.ops.svlm.frames_to_patches(frames_thwc, self.geo.patch_size, self.geo.temporal_patch_size, self.geo.spatial_merge_size)
+        grid = torch.tensor([[frames_thwc.shape[0] // self.geo.temporal_patch_size, frames_thwc.shape[1] // self.geo.patch_size,
+                              frames_thwc.shape[2] // self.geo.patch_size]], dtype=torch.long)
+        ids = torch.tensor([prompt_ids], dtype=torch.long, device=self.dev)
+        ids = torch.cat([self.prev, ids if self.prev[0, -1].item() != 198 else ids[:, 1:]], dim=1)          # inference.py:397-406
+        self.pixels.append(None)
+        self.args.input_ids = ids
+        self.args.video_grid_thw = torch.cat([self.args.video_grid_thw, grid.to(self.dev)], dim=0)         # grows, as in the reference (:415)
+        n_in = ids.shape[1]
+        t0 = time.perf_counter()
+        out = self.model.generate(input_ids=ids, pixel_values_videos=px, video_grid_thw=grid, past_key_values=self.past,
+                                  max_new_tokens=NEW_TOKENS, use_cache=True, return_dict_in_generate=True, streaming_args=self.args,
+                                  pad_token_id=151645, suppress_tokens=self.sup, **self.gen_kwargs)
+        t_gen = time.perf_counter() - t0
+        seq = out.sequences
+        if seq[0, -1].item() != 151645:                                                                    # inference.py:457-459
+            seq = torch.cat([seq, torch.tensor([[151645]], device=self.dev)], dim=1)
+        self.past = out.past_key_values
+        self.prev = seq.clone()
+        new = seq.shape[1] - n_in
+        self.history.append({"role": "assistant", "content": "x " * new + "..."})
+        self.timing.append({"PKV": t_pkv, "GEN": t_gen, "new_tokens": new})
+        self.i += 1
+        return new
+
+
+DEFAULT_POLICY = {"window_size": 16, "text_round": 16, "text_sink": 512, "text_sliding_window": 512}
+
+
+def config3_sweep(pk, dev, sizes=(4096, 8192, 16384, 32768, 65536)):
+    """BASELINE.json configs[2]: KV compaction + contiguous-RoPE, split-KV decode attention and chunk-prefill attention at retained
+    cache lengths 4k..64k (7B geometry, bf16), each as a fraction of its roofline, under the same clock sampler as the headline.
+    Split counts are the engine's own heuristics.  (benchmarks/microbench.py adds the reference's library calls on the same GPU.)"""
+    from streaming_vlm_b200 import _abi
+    from streaming_vlm_b200.config import QWEN25VL_7B as G
+    from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
+    L, H, HQ, D = G.num_layers, G.num_kv_heads, G.num_heads, G.head_dim
+    scale = 1.0 / math.sqrt(D)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return statistics.median(ts)
+
+    points = []
+    with ClockSampler(dev.index or 0) as clk:
+        for n in sizes:
+            cap = n + 512
+            c = StreamingCache(G, cap, dev)
+            c.arena[0].normal_(0, 0.5)
+            c.pos.copy_(torch.arange(cap, dtype=torch.int32, device=dev).expand(3, cap) // 4)
+            # the steady-state 5-run gather scaled to n: sink 527 | drop 10 | text window | moved 10 | 2 | drop ~287 | rest
+            n_src = n + 297
+            runs, d = [], 0
+            for s_, l in [(0, 527), (537, 500), (1314, 10), (1037, 2), (1327, n_src - 1327)]:
+                runs.append((s_, d, l))
+                d += l
+            keep = d
+            rec = {"retained_tokens": keep}
+            t = timed(lambda: _abi.kv_compact_rope(c.view, 0, runs, c.pos, c.cos_table, c.sin_table, c.section))
+            byt = 2.5 * keep * G.kv_bytes_per_token
+            rec["kv_compact_rope"] = {"us": t * 1e6, "GBs": byt / t / 1e9, "frac": byt / t / 1e9 / pk["hbm_gbs"], "bound": "hbm"}
+            q1 = torch.randn(1, HQ, D, device=dev).to(torch.bfloat16)
+            o1 = torch.empty_like(q1)
+            kv_dev = torch.tensor([keep], dtype=torch.int32, device=dev)
+            n_tiles = (keep + 128) // 128
+            splits = max(1, min(148 // H, -(-n_tiles // 2)))                      # StreamingEngine.decode_step
+            ws = torch.zeros(max(_abi.attn_workspace_bytes(1, HQ, D, splits), _abi.attn_workspace_bytes(512, HQ, D, 4)) // 4 + 16,
+                             dtype=torch.float32, device=dev)
+            t = timed(lambda: [_abi.attn_causal(c.view, 1, li, q1, o1, 1, HQ, cap, scale, splits, ws, kv_len_dev=kv_dev) for li in range(L)]) / L
+            byt = keep * 2 * H * D * 2
+            rec["attn_decode"] = {"us_per_layer": t * 1e6, "splits": splits, "GBs": byt / t / 1e9, "frac": byt / t / 1e9 / pk["hbm_gbs"], "bound": "hbm"}
+            tq = 276
+            qp = torch.randn(tq, HQ, D, device=dev).to(torch.bfloat16)
+            op = torch.empty_like(qp)
+            sp = 1 if (-(-tq // (128 // G.group))) * H >= 74 or keep < 2048 else 2     # StreamingEngine.prefill
+            t = timed(lambda: [_abi.attn_causal(c.view, 1, li, qp, op, tq, HQ, keep, scale, sp, ws) for li in range(L)]) / L
+            fl = 4.0 * tq * (keep - tq / 2) * D * HQ
+            rec["attn_prefill"] = {"us_per_layer": t * 1e6, "splits": sp, "tq": tq, "TFLOPs": fl / t / 1e12, "frac": fl / t / 1e12 / pk["bf16_burst"],
+                                   "bound": "tensor"}
+            points.append(rec)
+            del c, ws
+            torch.cuda.empty_cache()
+    return {"workload": "configs[2]: retained cache 4k-64k tokens, 7B geometry (28 layers, 4 kv heads, 28 q heads, d 128), bf16; CUDA events "
+                        "around CUDA-graph replays of 28 layer launches (K/V of 28 layers >> L2 from 8k tokens up)",
+            "peaks": {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_burst": pk["bf16_burst"]}, "clocks": clk.summary(), "points": points}
+
+
 def run_gpu(args):
     from streaming_vlm_b200 import _abi, synthetic
     from streaming_vlm_b200.config import QWEN25VL_7B as G7
-    from streaming_vlm_b200.engine import StreamingEngine
+    from streaming_vlm_b200.engine import GREEDY
+    from streaming_vlm_b200.inference.generate.streaming_generate_qwen import _fast_path_engine
+    from streaming_vlm_b200.inference.qwen2_5.patch_model import convert_qwen2_5_to_streaming
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -377,40 +551,44 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     pk = peaks()
 
+    # ---- the reference-facing object: a stock HF model, patched; its `generate` runs on the session runner over the SAME tensors
     w = synthetic.random_weights(G7, seed=rank, device=dev)
-    engine = StreamingEngine(w, G7, capacity=8192, device=dev, suppress=synthetic.suppress_mask(G7.vocab))
+    model = convert_qwen2_5_to_streaming(build_hf_model(G7, w, dev))
     del w
+    engine = _fast_path_engine(model, None, 8192)
+    sup = synthetic.suppress_mask(G7.vocab).to(dev)
+    engine.set_suppress(sup)
     state = synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS, seed=rank)
     engine.load_state(state, seed=rank)
-    total = args.warmup + 2 * args.steps + 1
+    gen_kwargs = dict(do_sample=True, temperature=0.9, repetition_penalty=1.05) if args.generation == "reference" else dict(do_sample=False)
+    sess = DropInSession(model, G7, state, dev, sup, gen_kwargs)
+    n_legs = 3
+    total = args.warmup + n_legs * args.steps + 2
     base_i = engine.i
     # on-wire format of a chunk: 2 RGB frames, uint8 [T, H, W, 3] (what a video decoder hands over); the ingest kernel
     # (normalise + patchify, svlm_frames_to_patches) runs inside every timed step
-    fr_host = []
-    for k in range(total):
-        fr_host.append(synthetic.frames(base_i + k).permute(0, 2, 3, 1).contiguous().pin_memory())
+    fr_host = [synthetic.frames(base_i + k).permute(0, 2, 3, 1).contiguous().pin_memory() for k in range(total)]
     fr_dev = [f.to(dev) for f in fr_host[:args.warmup + args.steps]]
-    grid = (1, fr_host[0].shape[1] // G7.patch_size, fr_host[0].shape[2] // G7.patch_size)
     prompts = [synthetic.round_prompt(base_i + k, seed=rank) for k in range(total)]
+    grid = (1, fr_host[0].shape[1] // G7.patch_size, fr_host[0].shape[2] // G7.patch_size)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(k0, n, host_pixels):
+    def run_dropin(k0, n, host_pixels):
         lat, toks = [], 0
         for k in range(k0, k0 + n):
             t0 = time.perf_counter()
             fr = fr_host[k].to(dev, non_blocking=True) if host_pixels else fr_dev[k]
-            r = engine.step(prompts[k], None, grid, sync_timing=False, frames=fr)
+            toks += min(sess.step(prompts[k], fr), NEW_TOKENS)
             torch.cuda.current_stream().synchronize()
             lat.append(time.perf_counter() - t0)
-            toks += min(len(r["new_tokens"]), NEW_TOKENS)
         return lat, toks
 
-    run_steps(0, args.warmup, False)
-    # ---- timed region 1: inputs resident in HBM
+    run_dropin(0, args.warmup, False)
+    # ---- timed region 1 (value): drop-in API, frames resident in HBM
     barrier()
     launches0 = engine.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -418,30 +596,50 @@ def run_gpu(args):
         if args.profile_range:
             torch.cuda.profiler.start()
         e0.record()
-        lat, toks = run_steps(args.warmup, args.steps, False)
+        lat, toks = run_dropin(args.warmup, args.steps, False)
         e1.record()
         barrier()
         if args.profile_range:
             torch.cuda.profiler.stop()
-    t_dev = e0.elapsed_time(e1) * 1e-3
-    launches = engine.launches - launches0
-    # ---- timed region 2: end to end, uint8 frames from pinned host memory, token ids read back every step
+        t_dev = e0.elapsed_time(e1) * 1e-3
+        launches = engine.launches - launches0
+        gen_s = sum(t["GEN"] for t in sess.timing[-args.steps:])
+        gen_tok = sum(t["new_tokens"] for t in sess.timing[-args.steps:])
+        # ---- timed region 2 (e2e): drop-in API, uint8 frames from pinned host memory, ids up / tokens down through the host
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        lat2, toks2 = run_dropin(args.warmup + args.steps, args.steps, True)
+        f1.record()
+        barrier()
+        t_e2e = f0.elapsed_time(f1) * 1e-3
+    n_ids = int(sess.prev.shape[1])
+    # ---- the same stream continued through StreamingEngine.step directly (greedy): what the drop-in costs on top of the engine
+    engine.prev_ids = sess.prev[0].cpu().numpy()
+    engine.history, engine.clips, engine.pixels, engine.i = sess.history, sess.clips, sess.pixels, sess.i
+    engine.grids = [tuple(grid)] * (len(state["grids"]) + sess.i - base_i)
+    engine._grids_uploaded = None
+    engine.gen = GREEDY
+    k_eng = args.warmup + 2 * args.steps
+    engine.step(prompts[k_eng], None, grid, sync_timing=False, frames=fr_host[k_eng].to(dev))          # captures the greedy graphs
+    engine.step(prompts[k_eng + 1], None, grid, sync_timing=False, frames=fr_host[k_eng + 1].to(dev))
     barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    lat2, toks2 = run_steps(args.warmup + args.steps, args.steps, True)
-    f1.record()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    toks3 = 0
+    for k in range(k_eng + 2, k_eng + 2 + args.steps):
+        r = engine.step(prompts[k], None, grid, sync_timing=False, frames=fr_host[k].to(dev, non_blocking=True))
+        toks3 += min(len(r["new_tokens"]), NEW_TOKENS)
+    g1.record()
     barrier()
-    t_e2e = f0.elapsed_time(f1) * 1e-3
+    t_eng = g0.elapsed_time(g1) * 1e-3
     if dist is not None:
-        tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_e2e, t_eng], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+        t_dev, t_e2e, t_eng = float(tt[0]), float(tt[1]), float(tt[2])
 
-    gen_s = sum(t["GEN"] for t in engine.timing[-args.steps:])
-    n_ids = len(engine.prev_ids)
-    h2d = fr_host[0].numel() + n_ids * 8
-    d2h = NEW_TOKENS * 8
+    h2d = fr_host[0].numel() + n_ids * 8            # uint8 frames + the int64 ids the loop uploads (torch.tensor(prompt), pruned ids)
+    d2h = n_ids * 8 + NEW_TOKENS * 8                # the loop reads the ids back for eviction planning, plus one id per token
     line = None
     if rank == 0:
         roofs = kernel_rooflines(engine, pk)
@@ -453,16 +651,27 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
                 "decode_tok_s": world * toks / t_dev, "p50_chunk_ms": 1e3 * statistics.median(lat), "p99_chunk_ms": 1e3 * max(lat),
+                # the reference's own protocol number (eval/efficiency/efficiency_test.py:88-98): GEN section / decoded tokens
+                "gen_s_per_token": gen_s / max(gen_tok, 1),
                 "e2e": {"value": world * args.steps * FRAMES_PER_CHUNK / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "p50_chunk_ms": 1e3 * statistics.median(lat2), "decode_tok_s": world * toks2 / t_e2e},
+                        "p50_chunk_ms": 1e3 * statistics.median(lat2), "decode_tok_s": world * toks2 / t_e2e,
+                        "api": "process_past_kv + patched HF model.generate (host frames, host ids)"},
+                "engine_api": {"value": world * args.steps * FRAMES_PER_CHUNK / t_eng, "unit": UNIT, "ms_per_step": 1e3 * t_eng / args.steps,
+                               "decode_tok_s": world * toks3 / t_eng, "generation": "greedy", "api": "StreamingEngine.step (host frames)"},
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "roofline_kernels": roofs,
-                "kv_len": engine.cache.seq_len, "streams_per_gpu": 1}
+                "kv_len": engine.cache.seq_len, "streams_per_gpu": 1,
+                "graphs": {"prefill": len(engine._pf_graphs), "decode": len(engine._graphs), "vit": len(engine._vit_graphs)}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, desc, _ = cpu_chunk_sample(cores, steps=1, warmup=1)
+            v, desc, _ = cpu_chunk_sample(cores, steps=1, warmup=0, budget_s=60.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         else:
             line["cpu_baseline"] = None
+        if world == 1 and not args.no_sweep:
+            try:
+                line["config3_sweep"] = config3_sweep(pk, dev)
+            except Exception as exc:   # noqa: BLE001   (an extra leg must never cost the headline line)
+                line["config3_sweep"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if args.streams > 1:
         # extra leg: it must never cost the headline line (every rank still takes part in the all-reduce below)
         try:
@@ -490,6 +699,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="streams per GPU of the extra multi-stream leg (BASELINE configs[3]); 1 = skip")
+    ap.add_argument("--generation", default="reference", choices=["reference", "greedy"],
+                    help="token selection of the timed drop-in legs: the reference's sampling config or greedy")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[2] 4k-64k kernel sweep")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around timed region 1 (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl != "reference":

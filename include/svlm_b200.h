@@ -159,6 +159,16 @@ int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int 
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (6a) Token embedding fused with the splice of the video embeddings.
+ * Replaces: qwen2_5/model_forward.py:58 (embed_tokens) + :80-93 (count check, masked_scatter of video_embeds).
+ *   ids [n_tokens] int64 device; embed bf16 [vocab][hidden]; video bf16 [n_video][hidden] or NULL
+ *   out bf16 [n_tokens][hidden]: row t = video[r] if ids[t] == video_token_id (r = placeholders before t), else embed[ids[t]]
+ *   status (int32 device, may be NULL): bit 8 = more placeholders than video rows, bit 16 = id outside the vocabulary
+ * ------------------------------------------------------------------------------------- */
+int svlm_embed_tokens(const int64_t* ids, int n_tokens, int64_t video_token_id, const void* embed, int64_t vocab,
+                      const void* video, int n_video, int hidden, void* out, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (6b) Elementwise glue of the prefill / ViT blocks, fused (bf16 in / out, fp32 arithmetic).
  * svlm_add_rmsnorm replaces `hidden = residual + x` followed by the next RMSNorm
  *   (qwen2_5/language_forward.py:290-295, qwen2_5/vision_forward.py:46-52): out_sum = bf16(a + b) (b and out_sum may
@@ -196,6 +206,26 @@ int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, 
 int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
                         int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
                         int32_t* next_pos, void* stream);
+/* The same kernel with the reference's generation config (inference/inference.py:41-42, 426-451: do_sample=True,
+ * temperature=0.9, repetition_penalty=1.05; the logits processors and the multinomial draw of
+ * generate/streaming_generate_qwen.py:73-99) fused into the lm_head epilogue, per vocabulary row n:
+ *     score = fp32(bf16 logit);  if seen[n]: score = score < 0 ? score * penalty : score / penalty   (HF RepetitionPenaltyLogitsProcessor)
+ *     score = score / temperature (skipped when temperature == 1)                                    (HF TemperatureLogitsWarper)
+ *     Both divisions are evaluated the way ATen evaluates `tensor / python_scalar` on the GPU, where the reference runs them: a
+ *     multiplication with float(1.0 / double(scalar)).
+ *     do_sample: token = argmax_n(score_n + Gumbel noise_n)  -- an exact sample of softmax(score) (Gumbel-max), noise from
+ *                Philox4x32-10 with key (rng_state[0], rng_state[1]) and counter (n, rng_state[2]); else first argmax of score.
+ * `seen` (uint8 [N], svlm_mark_seen) is the set of ids in the sequence so far; the chosen token is added to it and the step
+ * word rng_state[2] is incremented on the device (rng_state: uint32 [4] in device memory: seed lo, seed hi, step, reserved),
+ * so a CUDA-graph replay per token needs no host involvement and a new seed needs no new graph.  scores_out (fp32 [N] or NULL)
+ * receives the processed scores (HF `output_scores`), -inf for suppressed rows. */
+int svlm_lm_head_sample(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
+                        int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
+                        int32_t* next_pos, uint8_t* seen, double repetition_penalty, double temperature, int do_sample,
+                        uint32_t* rng_state, float* scores_out, void* stream);
+/* seen[ids[i]] = 1 for i < n (after clearing all `vocab` bytes when clear_first != 0): the repetition-penalty target set of
+ * the ids already in the sequence (generate/streaming_generate_qwen.py:75 passes the full `input_ids`). */
+int svlm_mark_seen(const int64_t* ids, int n, uint8_t* seen, int64_t vocab, int clear_first, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (8) Decode step of SEVERAL independent streams in one launch (the reference runs one stream per process,

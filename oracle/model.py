@@ -112,9 +112,14 @@ class Session:
     the caller as token-id lists (no tokenizer exists offline)."""
 
     def __init__(self, w, geo, window_size=16, text_round=16, text_sink=512, text_sliding_window=512,
-                 max_new_tokens=20, suppress=None, assistant_start_bias=3, assistant_end_bias=2, pos_mode="shrink"):
+                 max_new_tokens=20, suppress=None, assistant_start_bias=3, assistant_end_bias=2, pos_mode="shrink",
+                 repetition_penalty=1.0, temperature=1.0):
         assert pos_mode in ("append", "shrink"), "pos_mode must be in ['append', 'shrink']"      # streaming_args.py:5
         self.pos_mode = pos_mode
+        # logits processors of the reference's generate call (inference.py:41-42, 433-437): HF RepetitionPenaltyLogitsProcessor
+        # over the whole `input_ids` so far, then TemperatureLogitsWarper (streaming_generate_qwen.py:75); token selection here
+        # stays the argmax of the processed scores (the multinomial draw is not reproducible across RNG implementations)
+        self.repetition_penalty, self.temperature = float(repetition_penalty), float(temperature)
         self.pos_state = {"last_cache_position": -1}
         self.w, self.geo = w, geo
         self.window_size, self.text_round = window_size, text_round
@@ -172,6 +177,12 @@ class Session:
                                    taps if n_fwd == 0 else None, timers, self.pos_mode, self.pos_state)
             full = full + [0]                   # F.pad(ids, (0,1)) after every forward
             n_fwd += 1
+            if self.repetition_penalty != 1.0:
+                seen = torch.tensor(seq, dtype=torch.long)
+                score = logits[seen]
+                logits = logits.scatter(0, seen, torch.where(score < 0, score * self.repetition_penalty, score / self.repetition_penalty))
+            if self.temperature != 1.0:
+                logits = logits / self.temperature
             if self.suppress is not None:
                 logits = logits.masked_fill(self.suppress, float("-inf"))
             step_logits.append(logits)

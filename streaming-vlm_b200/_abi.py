@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
-           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
            "svlm_frames_to_patches", "svlm_frames_resize_bicubic",
            "svlm_kv_compact_rope_host"]
 
@@ -96,6 +96,9 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemv_bf16.argtypes = [vp, vp, vp, c_float, vp, vp, vp, c_int, c_int, c_int, vp]
     L.svlm_gemv_qkv_rope_append.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.svlm_lm_head_sample.argtypes = [vp, vp, vp, c_float, vp, c_int, c_int, vp, vp, vp, vp, vp, vp, ctypes.c_double, ctypes.c_double, c_int, vp, vp, vp]
+    L.svlm_mark_seen.argtypes = [vp, c_int, vp, c_int64, c_int, vp]
+    L.svlm_embed_tokens.argtypes = [vp, c_int, c_int64, vp, c_int64, vp, c_int, c_int, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
     L.svlm_frames_resize_bicubic.argtypes = [vp, c_int, c_int, c_int, vp, c_int, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp]
     L.svlm_frames_to_patches.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), vp, c_int, vp]
@@ -172,9 +175,10 @@ def mrope_positions(ids: torch.Tensor, n: int, grids: torch.Tensor, n_grids: int
 
 def qkv_rope_append(arena: ArenaView, buffer: int, layer: int, q, k, v, n_tokens: int, q_heads: int, q_out, start: int, pos,
                     cos_table, sin_table, section, start_dev=None, text_pos_dev=None):
+    """q_heads == 0 (q = q_out = None): append-only, K_raw / K_rot / V rows of the new tokens."""
     _req_cuda(q, k, v, q_out)
-    check(lib().svlm_qkv_rope_append(arena.ref, buffer, layer, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0),
-                                     v.stride(0), n_tokens, q_heads, q_out.data_ptr(), start, _ptr(start_dev), _ptr(pos),
+    check(lib().svlm_qkv_rope_append(arena.ref, buffer, layer, _ptr(q), k.data_ptr(), v.data_ptr(), 0 if q is None else q.stride(0), k.stride(0),
+                                     v.stride(0), n_tokens, q_heads, _ptr(q_out), start, _ptr(start_dev), _ptr(pos),
                                      0 if pos is None else pos.stride(0), _ptr(text_pos_dev), cos_table.data_ptr(),
                                      sin_table.data_ptr(), cos_table.shape[0], i32_array(section), _stream()),
           "svlm_qkv_rope_append")
@@ -237,6 +241,39 @@ def lm_head_argmax(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, 
     check(lib().svlm_lm_head_argmax(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
                                     key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
                                     next_pos.data_ptr(), _stream()), "svlm_lm_head_argmax")
+
+
+def lm_head_sample(w, x, norm_weight, eps, suppress_u8, key_scratch, token_out, kv_len, kv_after, next_pos, seen=None,
+                   repetition_penalty: float = 1.0, temperature: float = 1.0, do_sample: bool = False, rng_state=None, scores_out=None):
+    """lm_head with the reference's generation config fused in (repetition penalty over `seen`, temperature, Gumbel-max
+    sampling; `rng_state`: int32/uint32 [4] on the device = seed lo, seed hi, step, reserved); see include/svlm_b200.h."""
+    _req_cuda(w, x, key_scratch, token_out, seen, rng_state, scores_out)
+    check(lib().svlm_lm_head_sample(w.data_ptr(), x.data_ptr(), _ptr(norm_weight), eps, _ptr(suppress_u8), w.shape[0], w.shape[1],
+                                    key_scratch.data_ptr(), token_out.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
+                                    next_pos.data_ptr(), _ptr(seen), float(repetition_penalty), float(temperature), 1 if do_sample else 0,
+                                    _ptr(rng_state), _ptr(scores_out), _stream()), "svlm_lm_head_sample")
+
+
+def rng_words(seed: int):
+    """(seed lo, seed hi, step = 0, 0) as signed 32-bit values for an int32 tensor."""
+    def s32(v):
+        v &= 0xFFFFFFFF
+        return v - (1 << 32) if v >= (1 << 31) else v
+    return [s32(seed), s32(seed >> 32), 0, 0]
+
+
+def mark_seen(ids, n: int, seen, clear_first: bool = True):
+    _req_cuda(ids, seen)
+    assert ids.dtype == torch.int64 and seen.dtype == torch.uint8
+    check(lib().svlm_mark_seen(ids.data_ptr(), n, seen.data_ptr(), seen.numel(), 1 if clear_first else 0, _stream()), "svlm_mark_seen")
+
+
+def embed_tokens(ids, n: int, embed, video, n_video: int, out, status=None, video_token_id: int = 151656):
+    """out[t] = video[rank(t)] where ids[t] is the video placeholder, else embed[ids[t]] (model_forward.py:58, 87-93)."""
+    _req_cuda(ids, embed, video, out, status)
+    assert ids.dtype == torch.int64 and embed.is_contiguous() and out.is_contiguous() and (video is None or video.is_contiguous())
+    check(lib().svlm_embed_tokens(ids.data_ptr(), n, video_token_id, embed.data_ptr(), embed.shape[0], _ptr(video), n_video, embed.shape[1],
+                                  out.data_ptr(), _ptr(status), _stream()), "svlm_embed_tokens")
 
 
 def make_slots(caches, row_devs, pos_devs, kv_len_devs):

@@ -123,7 +123,8 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
     // device-side length are its outputs
     pdl_wait();
 
-    const int kv_len = p.kv_len_dev[strm] ? __ldg(p.kv_len_dev[strm]) : p.kv_len;
+    // the host value is the documented upper bound (<= arena capacity): a device-side length beyond it never reaches the TMA
+    const int kv_len = p.kv_len_dev[strm] ? min(__ldg(p.kv_len_dev[strm]), p.kv_len) : p.kv_len;
     const int n_total = (kv_len + DEC_BN - 1) / DEC_BN;
     const int tps = (n_total + p.num_splits - 1) / p.num_splits;
     const int my_begin = split * tps;

@@ -40,7 +40,36 @@ struct GemvParams {
     const uint16_t* cos_tab;    // bf16 [rows][64]
     const uint16_t* sin_tab;
     int tab_rows;
+    // ARGMAX with the reference's generation config (inference.py:41-42, 433-437: repetition penalty, temperature, sampling)
+    const uint8_t* seen;        // [N] 1 = id occurs in the sequence so far (repetition penalty target set); NULL = no penalty
+    // HF RepetitionPenaltyLogitsProcessor: score < 0 ? score * penalty : score / penalty; TemperatureLogitsWarper: score / temperature.
+    // The reference evaluates both on the GPU, where ATen divides by a Python scalar as a multiplication with the reciprocal
+    // float(1.0 / double(b)) (BinaryDivTrueKernel.cu, `is_cpu_scalar(2)` branch): the same arithmetic is used here.
+    float penalty, inv_penalty, inv_temperature;
+    int scale_temperature;
+    int do_sample;              // 1: Gumbel-max sample of softmax(score); 0: argmax of the processed score
+    const uint32_t* rng;        // device [4]: Philox key (seed lo, seed hi), counter word 1 = step (advanced by decode_finalize_kernel), reserved
+    float* scores_out;          // [N] processed scores (HF `output_scores`), or NULL
 };
+
+// Philox4x32-10 (Salmon et al.), counter (c0, c1, 0, 0), key = seed: one uniform per (vocabulary row, step)
+__device__ __forceinline__ uint32_t philox_u32(uint32_t c0, uint32_t c1, unsigned long long seed) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), c2 = 0u, c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+// Gumbel(0, 1) noise: argmax_n(score_n + g_n) is an exact sample of softmax(score) (Gumbel-max)
+__device__ __forceinline__ float gumbel_noise(uint32_t bits) {
+    const float u = ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1), 24 bits
+    return -logf(-logf(u));
+}
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
     const uint32_t* a = &w.x;
@@ -231,8 +260,15 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
         if (n < p.N) {
             if (MODE == GEMV_ARGMAX) {
                 if (!(p.suppress && p.suppress[n])) {
-                    const float logit = round_bf16(v);
-                    mine = ((unsigned long long)ordered_f32(logit) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                    float score = round_bf16(v);                                       // the lm_head output is bf16, upcast to fp32
+                    if (p.seen && p.seen[n]) score = score < 0.f ? __fmul_rn(score, p.penalty) : __fmul_rn(score, p.inv_penalty);
+                    if (p.scale_temperature) score = __fmul_rn(score, p.inv_temperature);
+                    if (p.scores_out) p.scores_out[n] = score;
+                    if (p.do_sample)
+                        score += gumbel_noise(philox_u32((uint32_t)n, p.rng[2], (unsigned long long)p.rng[0] | ((unsigned long long)p.rng[1] << 32)));
+                    mine = ((unsigned long long)ordered_f32(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                } else if (p.scores_out) {
+                    p.scores_out[n] = -INFINITY;
                 }
             } else if (MODE == GEMV_SWIGLU) {
                 const float gt = round_bf16(v), up = round_bf16(v2);
@@ -258,11 +294,15 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
 }
 
 // token id + device-side counters of the decode loop (kv length before / after the next step, next text position)
-__global__ void decode_finalize_kernel(unsigned long long* key, int64_t* tok, int32_t* kv_len, int32_t* kv_after, int32_t* next_pos) {
+__global__ void decode_finalize_kernel(unsigned long long* key, int64_t* tok, int32_t* kv_len, int32_t* kv_after, int32_t* next_pos,
+                                       uint8_t* seen, uint32_t* rng) {
     pdl_wait();
     const unsigned long long k = *key;
-    *tok = (int64_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+    const uint32_t t = 0xffffffffu - (uint32_t)(k & 0xffffffffull);
+    *tok = (int64_t)t;
     *key = 0ull;
+    if (seen) seen[t] = 1;              // the new token joins the repetition-penalty set
+    if (rng) rng[2] = rng[2] + 1;       // next token of the turn draws fresh noise
     const int n = *kv_len + 1;
     *kv_len = n;
     *kv_after = n + 1;
@@ -375,18 +415,38 @@ extern "C" int svlm_gemv_bf16(const void* W, const void* x, const void* norm_wei
     }
 }
 
-extern "C" int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
+extern "C" int svlm_lm_head_sample(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
                                    int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
-                                   int32_t* next_pos, void* stream) {
+                                   int32_t* next_pos, uint8_t* seen, double repetition_penalty, double temperature, int do_sample,
+                                   uint32_t* rng_state, float* scores_out, void* stream) {
     int rc = check_device();
     if (rc) return rc;
     if ((rc = gemv_common_checks(W, x, key_scratch, N, K))) return rc;
     SVLM_REQUIRE(token_out && kv_len && kv_after && next_pos, "NULL counter argument");
+    SVLM_REQUIRE(repetition_penalty > 0.0 && temperature > 0.0, "repetition_penalty (%f) and temperature (%f) must be positive",
+                 repetition_penalty, temperature);
+    SVLM_REQUIRE(!do_sample || rng_state != nullptr, "sampling needs the device-side RNG state");
     GemvParams p{(const uint16_t*)W, (const uint16_t*)x, (const uint16_t*)norm_weight, eps, nullptr, nullptr, nullptr, N, K, suppress,
                  (unsigned long long*)key_scratch};
+    p.seen = repetition_penalty != 1.0 ? seen : nullptr;
+    p.penalty = (float)repetition_penalty;
+    p.inv_penalty = (float)(1.0 / repetition_penalty);
+    p.inv_temperature = (float)(1.0 / temperature);
+    p.scale_temperature = temperature != 1.0 ? 1 : 0;
+    p.do_sample = do_sample ? 1 : 0;
+    p.rng = rng_state;
+    p.scores_out = scores_out;
     if ((rc = dispatch_rw<GEMV_ARGMAX>(p, (cudaStream_t)stream))) return rc;
-    launch_pdl(PDL_OTHER, decode_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)key_scratch, token_out, kv_len, kv_after, next_pos);
+    launch_pdl(PDL_OTHER, decode_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)key_scratch, token_out, kv_len,
+               kv_after, next_pos, seen, do_sample ? rng_state : nullptr);
     return launch_status("decode_finalize_kernel");
+}
+
+extern "C" int svlm_lm_head_argmax(const void* W, const void* x, const void* norm_weight, float eps, const uint8_t* suppress, int N,
+                                   int K, uint64_t* key_scratch, int64_t* token_out, int32_t* kv_len, int32_t* kv_after,
+                                   int32_t* next_pos, void* stream) {
+    return svlm_lm_head_sample(W, x, norm_weight, eps, suppress, N, K, key_scratch, token_out, kv_len, kv_after, next_pos, nullptr, 1.0,
+                               1.0, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int svlm_gemv_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, const void* W, const void* x,

@@ -536,6 +536,52 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const uint16_t* __restrict_
     *reinterpret_cast<uint4*>(out + r * out_stride + c) = o;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// embed_tokens: token embedding lookup fused with the splice of the video embeddings (model_forward.py:58, :87-93
+// `masked_scatter`): row t of the output is video[rank(t)] when ids[t] is the video placeholder (rank = number of
+// placeholders before t among these ids), else embed[ids[t]].  One CTA per token row; the placeholder layout is read
+// on the device, so a CUDA graph of the chunk prefill does not depend on it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_tokens_kernel(const int64_t* __restrict__ ids, int n, int64_t video_id, int64_t vocab,
+                                                            const uint16_t* __restrict__ embed, const uint16_t* __restrict__ video,
+                                                            int n_video, int hidden, uint16_t* __restrict__ out, int32_t* __restrict__ status) {
+    __shared__ int cnt[4];
+    const int t = blockIdx.x;
+    const int64_t id = ids[t];
+    const uint16_t* src;
+    if (id == video_id && video != nullptr) {
+        int c = 0;
+        for (int i = threadIdx.x; i < t; i += 128) c += ids[i] == video_id;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = c;
+        __syncthreads();
+        const int rank = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        if (rank >= n_video) {                      // more placeholders than feature rows: flagged, row zeroed
+            if (threadIdx.x == 0 && status) atomicOr(status, 8);
+            for (int k = threadIdx.x * 8; k < hidden; k += 128 * 8) *reinterpret_cast<uint4*>(out + (int64_t)t * hidden + k) = make_uint4(0, 0, 0, 0);
+            return;
+        }
+        src = video + (int64_t)rank * hidden;
+    } else {
+        const int64_t row = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        if (row != id && threadIdx.x == 0 && status) atomicOr(status, 16);
+        src = embed + row * hidden;
+    }
+    for (int k = threadIdx.x * 8; k < hidden; k += 128 * 8)
+        *reinterpret_cast<uint4*>(out + (int64_t)t * hidden + k) = __ldg(reinterpret_cast<const uint4*>(src + k));
+}
+
+// seen[ids[i]] = 1: the token set the repetition penalty applies to (HF RepetitionPenaltyLogitsProcessor gathers the scores at
+// `input_ids`, generate/streaming_generate_qwen.py:75)
+__global__ void __launch_bounds__(256) mark_seen_kernel(const int64_t* __restrict__ ids, int n, uint8_t* __restrict__ seen, int64_t vocab) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        const int64_t id = ids[i];
+        if (id >= 0 && id < vocab) seen[id] = 1;
+    }
+}
+
 static int make_tables(RopeTables* t, const void* cos_table, const void* sin_table, int rows, const int32_t* sec, int D) {
     SVLM_REQUIRE(cos_table && sin_table && rows > 0, "rope tables missing");
     SVLM_REQUIRE(sec != nullptr, "mrope_section is NULL");
@@ -609,8 +655,9 @@ extern "C" int svlm_qkv_rope_append(const svlm_arena_t* arena, int buffer, int l
     if ((rc = validate_arena(arena))) return rc;
     SVLM_REQUIRE(buffer == 0 || buffer == 1, "buffer must be 0 or 1");
     SVLM_REQUIRE(layer >= 0 && layer < arena->layers, "layer %d out of range", layer);
-    SVLM_REQUIRE(q && k && v && q_out, "NULL tensor argument");
-    SVLM_REQUIRE(n_tokens >= 0 && q_heads > 0, "bad n_tokens / q_heads");
+    // q_heads == 0: append-only (K_raw / K_rot / V rows of the new tokens, no query), the route StreamingCache.update takes
+    SVLM_REQUIRE(k && v && (q_heads == 0 || (q && q_out)), "NULL tensor argument");
+    SVLM_REQUIRE(n_tokens >= 0 && q_heads >= 0, "bad n_tokens / q_heads");
     SVLM_REQUIRE(start >= 0 && start + n_tokens <= arena->capacity, "append of %d tokens at %d exceeds capacity %d", n_tokens, start,
                  arena->capacity);
     SVLM_REQUIRE(text_pos_dev != nullptr || (pos != nullptr && pos_stride >= start + n_tokens), "positions missing or too short");
@@ -736,4 +783,28 @@ extern "C" int svlm_swiglu(const void* gate_up, void* out, int rows, int M, int6
     swiglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)gate_up, (uint16_t*)out, rows, M,
                                                                                      gate_up_row_stride, out_row_stride);
     return launch_status("swiglu_kernel");
+}
+
+extern "C" int svlm_embed_tokens(const int64_t* ids, int n_tokens, int64_t video_token_id, const void* embed, int64_t vocab, const void* video,
+                                 int n_video, int hidden, void* out, int32_t* status, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(ids && embed && out, "NULL tensor argument");
+    SVLM_REQUIRE(n_tokens >= 0 && vocab > 0 && n_video >= 0, "bad n_tokens / vocab / n_video");
+    SVLM_REQUIRE(hidden > 0 && hidden % 8 == 0, "hidden %d must be a positive multiple of 8", hidden);
+    SVLM_REQUIRE((((uintptr_t)embed | (uintptr_t)video | (uintptr_t)out) & 15) == 0, "embed / video / out must be 16-byte aligned");
+    if (n_tokens == 0) return SVLM_OK;
+    embed_tokens_kernel<<<n_tokens, 128, 0, (cudaStream_t)stream>>>(ids, n_tokens, video_token_id, vocab, (const uint16_t*)embed,
+                                                                   (const uint16_t*)video, n_video, hidden, (uint16_t*)out, status);
+    return launch_status("embed_tokens_kernel");
+}
+
+extern "C" int svlm_mark_seen(const int64_t* ids, int n, uint8_t* seen, int64_t vocab, int clear_first, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(seen && vocab > 0 && n >= 0 && (n == 0 || ids), "bad argument");
+    if (clear_first) SVLM_CUDA(cudaMemsetAsync(seen, 0, (size_t)vocab, (cudaStream_t)stream));
+    if (n == 0) return SVLM_OK;
+    mark_seen_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, n, seen, vocab);
+    return launch_status("mark_seen_kernel");
 }

@@ -25,6 +25,8 @@ from __future__ import annotations
 import math
 import os
 import time
+from collections import OrderedDict
+from dataclasses import dataclass
 
 import numpy as np
 import torch
@@ -89,12 +91,54 @@ class _VitPlan:
         self.cu_full = torch.tensor([i * h * w for i in range(t + 1)], dtype=torch.int32, device=device)
 
 
+@dataclass(frozen=True)
+class GenConfig:
+    """Token selection of one turn: the reference generates with `do_sample=True, temperature=0.9, repetition_penalty=1.05`
+    (`inference.py:41-42, 426-451`; logits processors + multinomial at `generate/streaming_generate_qwen.py:73-99`); greedy
+    (`do_sample=False`, penalty 1, temperature 1) is the parity mode.  All of it runs inside the lm_head kernel
+    (`svlm_lm_head_sample`); a frozen value because CUDA graphs are keyed on it."""
+    do_sample: bool = False
+    repetition_penalty: float = 1.0
+    temperature: float = 1.0
+    seed: int = None        # None: every turn draws from the engine's own stream (base seed + turn counter); an int pins the turn
+
+
+GREEDY = GenConfig()
+REFERENCE_SAMPLING = GenConfig(do_sample=True, repetition_penalty=1.05, temperature=0.9)
+PREFILL_BUCKET = 8          # chunk-prefill graphs are captured for token counts rounded up to a multiple of this
+
+
+class _GraphCache(OrderedDict):
+    """LRU-bounded map of CUDA graphs: the keys carry run-time values (token-count bucket, split count, live buffer,
+    generation config), so the number of captured graphs must not grow with the length of the stream."""
+
+    def __init__(self, limit):
+        super().__init__()
+        self.limit = limit
+        self.evictions = 0
+
+    def get(self, key):
+        v = super().get(key)
+        if v is not None:
+            self.move_to_end(key)
+        return v
+
+    def put(self, key, value):
+        self[key] = value
+        self.move_to_end(key)
+        while len(self) > self.limit:
+            self.popitem(last=False)
+            self.evictions += 1
+        return value
+
+
 class StreamingEngine:
     def __init__(self, weights: dict, geo: Geometry, capacity: int = 8192, device="cuda", window_size=DEFAULT_WINDOW_SIZE,
                  text_round=DEFAULT_TEXT_ROUND, text_sink=DEFAULT_TEXT_SINK, text_sliding_window=DEFAULT_TEXT_SLIDING_WINDOW,
                  max_new_tokens=MAX_TOKEN_PER_DURATION, suppress=None, assistant_start_bias=3, assistant_end_bias=2,
                  use_graph=True, decode_splits=None, prefill_splits=None, share_weights_from=None, pos_mode="shrink",
-                 max_position=None, tp_group=None):
+                 max_position=None, tp_group=None, gen: GenConfig = GREEDY, rebind=None, max_graphs: int = 24, cache=None,
+                 prefill_bucket: int = PREFILL_BUCKET):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         _abi.lib()
@@ -121,8 +165,13 @@ class StreamingEngine:
         self.pos_mode = pos_mode
         if pos_mode == "append" and max_position is None:
             max_position = 1 << 17
-        self.cache = StreamingCache(geo, capacity, self.device, max_position=max_position)
-        self._pos_upper = 0          # host-side upper bound of the largest position handed out (append mode)
+        if cache is not None:            # an arena the caller owns (the drop-in's `past_key_values`)
+            capacity = cache.capacity
+            self.cache = cache
+        else:
+            self.cache = StreamingCache(geo, capacity, self.device, max_position=max_position, pos_mode=pos_mode)
+        self.gen = gen
+        self.prefill_bucket = max(1, int(prefill_bucket))
         self.video_pixel_budget = (None, None)      # (min_pixels, max_pixels) per frame for `ingest`; None = keep sizes that fit the patch grid
         self.scale = 1.0 / math.sqrt(geo.head_dim)
         self.decode_splits = decode_splits or max(1, min((capacity + 127) // 128, 296 // geo.num_kv_heads))   # two CTAs per SM
@@ -131,7 +180,7 @@ class StreamingEngine:
             for name in ("w_patch", "vit", "vit_mlp_padded", "merger", "embed", "layers", "norm", "lm_head"):
                 setattr(self, name, getattr(share_weights_from, name))
         else:
-            self._prepare_weights(weights)
+            self._prepare_weights(weights, rebind)
         g = geo
         dev = self.device
         self.ws = torch.zeros(max(_abi.attn_workspace_bytes(1, g.num_heads, g.head_dim, self.decode_splits),
@@ -142,7 +191,7 @@ class StreamingEngine:
         self.tok_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._tok_ring = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
         self._tok_events = [torch.cuda.Event() for _ in range(2)]
-        self._graphs = {}
+        self._graphs = _GraphCache(max_graphs)
         self._dec_qkv = torch.zeros((g.num_heads + 2 * g.num_kv_heads) * g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_q = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         # side stream of the decode step: L2 prefetch of the o_proj weights and the head of the gate/up weights while the
@@ -155,10 +204,19 @@ class StreamingEngine:
         self._dec_part = torch.zeros(g.hidden, dtype=torch.bfloat16, device=dev)
         self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
         self._pf_ids = torch.zeros(1024, dtype=torch.int64, device=dev)
+        self._pf_last = torch.zeros(1, dtype=torch.int64, device=dev)          # row of the last real token in a padded prefill
+        self._pf_video = torch.zeros(1024, g.hidden, dtype=torch.bfloat16, device=dev)   # static home of the chunk's video embeddings
+        self._pf_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pf_status_pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._scratch_cnt = torch.zeros(3, dtype=torch.int32, device=dev)      # counters the prefill's lm_head launch may advance
+        self.seen = torch.zeros(g.vocab, dtype=torch.uint8, device=dev)        # ids in the sequence so far (repetition penalty)
+        self.rng_dev = torch.zeros(4, dtype=torch.int32, device=dev)           # Philox state: seed lo, seed hi, step (tokens drawn this turn)
+        self.base_seed, self._turns = 0, 0
+        self._rng_host = torch.zeros(4, dtype=torch.int32).pin_memory()
         self.suppress_u8 = None if self.suppress is None else self.suppress.to(torch.uint8).contiguous()
         self._vit_plans = {}
-        self._vit_graphs = {}
-        self._pf_graphs = {}
+        self._vit_graphs = _GraphCache(8)
+        self._pf_graphs = _GraphCache(max_graphs)
         # session state (reference: inference.py:297-303)
         self.prev_ids = None
         self.history, self.clips, self.pixels, self.grids = [], [], [], []
@@ -167,10 +225,28 @@ class StreamingEngine:
         self.launches = 0
 
     # ------------------------------------------------------------------ weights
-    def _prepare_weights(self, w):
+    def _prepare_weights(self, w, rebind=None):
+        """`w`: HF parameter names -> tensors (consumed).  Projections that the kernels read as ONE matrix ([q;k;v], [gate;up],
+        zero-padded ViT MLP) are fused here.  `rebind(name, view)`: called for every parameter that was fused, with a view of
+        the fused tensor that holds the same values -- `from_hf_model` uses it to re-point the live HF module's parameters, so
+        model and engine share ONE copy of the weights (everything that is not fused is aliased as is)."""
         g = self.geo
         dev = self.device
         mv = lambda t: t.to(dev).contiguous()
+        rb = rebind or (lambda name, view: None)
+
+        def fuse_rows(names, pad_to=None):
+            parts = [w.pop(n) for n in names]
+            rows = [p_.shape[0] for p_ in parts]
+            if pad_to is not None:
+                parts = [F.pad(p_, (0, 0, 0, pad_to - p_.shape[0])) if p_.dim() == 2 else F.pad(p_, (0, pad_to - p_.shape[0])) for p_ in parts]
+            fused = mv(torch.cat(parts, 0))
+            off = 0
+            for n, r, p_ in zip(names, rows, parts):
+                rb(n, fused[off:off + r])
+                off += p_.shape[0]
+            return fused
+
         v = "model.visual."
         pe = w.pop(v + "patch_embed.proj.weight")
         self.w_patch = mv(pe.reshape(pe.shape[0], -1))
@@ -180,16 +256,17 @@ class StreamingEngine:
         # silu(0) * 0 = 0 feeds zero columns of the down projection.
         mp = -(-g.vit_mlp // 64) * 64
         self.vit_mlp_padded = mp
-        padr = lambda t: F.pad(t, (0, 0, 0, mp - g.vit_mlp)) if t.dim() == 2 else F.pad(t, (0, mp - g.vit_mlp))
         for li in range(g.vit_depth):
             b = f"{v}blocks.{li}."
+            wd = mv(F.pad(w.pop(b + "mlp.down_proj.weight"), (0, mp - g.vit_mlp)))
+            rb(b + "mlp.down_proj.weight", wd[:, :g.vit_mlp])
             self.vit.append(dict(
                 n1=mv(w.pop(b + "norm1.weight")), n2=mv(w.pop(b + "norm2.weight")),
                 wqkv=mv(w.pop(b + "attn.qkv.weight")), bqkv=mv(w.pop(b + "attn.qkv.bias")),
                 wproj=mv(w.pop(b + "attn.proj.weight")), bproj=mv(w.pop(b + "attn.proj.bias")),
-                wgu=mv(torch.cat([padr(w.pop(b + "mlp.gate_proj.weight")), padr(w.pop(b + "mlp.up_proj.weight"))], 0)),
-                bgu=mv(torch.cat([padr(w.pop(b + "mlp.gate_proj.bias")), padr(w.pop(b + "mlp.up_proj.bias"))], 0)),
-                wd=mv(F.pad(w.pop(b + "mlp.down_proj.weight"), (0, mp - g.vit_mlp))), bd=mv(w.pop(b + "mlp.down_proj.bias"))))
+                wgu=fuse_rows([b + "mlp.gate_proj.weight", b + "mlp.up_proj.weight"], mp),
+                bgu=fuse_rows([b + "mlp.gate_proj.bias", b + "mlp.up_proj.bias"], mp),
+                wd=wd, bd=mv(w.pop(b + "mlp.down_proj.bias"))))
         self.merger = dict(ln=mv(w.pop(v + "merger.ln_q.weight")), w0=mv(w.pop(v + "merger.mlp.0.weight")),
                            b0=mv(w.pop(v + "merger.mlp.0.bias")), w2=mv(w.pop(v + "merger.mlp.2.weight")),
                            b2=mv(w.pop(v + "merger.mlp.2.bias")))
@@ -201,13 +278,69 @@ class StreamingEngine:
             a = b + "self_attn."
             self.layers.append(dict(
                 ln1=mv(w.pop(b + "input_layernorm.weight")), ln2=mv(w.pop(b + "post_attention_layernorm.weight")),
-                wqkv=mv(torch.cat([w.pop(a + "q_proj.weight"), w.pop(a + "k_proj.weight"), w.pop(a + "v_proj.weight")], 0)),
-                bqkv=mv(torch.cat([w.pop(a + "q_proj.bias"), w.pop(a + "k_proj.bias"), w.pop(a + "v_proj.bias")], 0)),
+                wqkv=fuse_rows([a + "q_proj.weight", a + "k_proj.weight", a + "v_proj.weight"]),
+                bqkv=fuse_rows([a + "q_proj.bias", a + "k_proj.bias", a + "v_proj.bias"]),
                 wo=mv(w.pop(a + "o_proj.weight")),
-                wgu=mv(torch.cat([w.pop(b + "mlp.gate_proj.weight"), w.pop(b + "mlp.up_proj.weight")], 0)),
+                wgu=fuse_rows([b + "mlp.gate_proj.weight", b + "mlp.up_proj.weight"]),
                 wd=mv(w.pop(b + "mlp.down_proj.weight"))))
         self.norm = mv(w.pop(lm + "norm.weight"))
-        self.lm_head = mv(w.pop("lm_head.weight"))
+        self.lm_head = mv(w.pop("lm_head.weight")) if "lm_head.weight" in w else self.embed      # tied embeddings
+
+    @classmethod
+    def from_hf_model(cls, model, capacity: int = 8192, **kwargs):
+        """Engine over the parameters of a live (patched) HF Qwen2.5-VL model, no second copy of the weights: unfused tensors
+        are aliased, fused ones ([q;k;v], [gate;up], padded ViT MLP) replace the module's own parameters by views of the fused
+        tensor.  This is what `convert_qwen2_5_to_streaming` + `generate` run on (reference `qwen2_5/patch_model.py:18-38`)."""
+        from .config import from_hf_config
+        geo = from_hf_config(model.config)
+        if geo.vit_kind != "qwen2_5":
+            raise RuntimeError("the session-runner fast path covers the Qwen2.5-VL tower; Qwen2-VL runs the patched eager forwards")
+        params = dict(model.named_parameters())
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("StreamingEngine.from_hf_model needs the model on a CUDA device (there is no CPU fallback)")
+        bad = [n for n, p_ in params.items() if p_.dtype != torch.bfloat16]
+        if bad:
+            raise RuntimeError(f"the svlm kernels compute in bf16; parameters such as {bad[0]} are {params[bad[0]].dtype}")
+
+        def rebind(name, view):
+            params[name].data = view
+
+        w = {n: p_.data for n, p_ in params.items()}
+        with torch.no_grad():
+            return cls(w, geo, capacity=capacity, device=dev, rebind=rebind, **kwargs)
+
+    # ------------------------------------------------------------------ drop-in plumbing
+    def adopt_cache(self, cache: StreamingCache):
+        """Run on another arena of the same geometry (`past_key_values` handed to the patched `generate`).  CUDA graphs bake the
+        arena's addresses in, so the captured ones are dropped."""
+        g = self.geo
+        if (cache.layers, cache.kv_heads, cache.head_dim) != (g.num_layers, g.num_kv_heads, g.head_dim):
+            raise RuntimeError("StreamingCache geometry does not match the model")
+        if cache.device != self.device:
+            raise RuntimeError(f"StreamingCache lives on {cache.device}, the model on {self.device}")
+        self.cache = cache
+        self._graphs.clear()
+        self._pf_graphs.clear()
+        self.decode_splits = max(1, min((cache.capacity + 127) // 128, 296 // g.num_kv_heads))
+        need = max(_abi.attn_workspace_bytes(1, g.num_heads, g.head_dim, self.decode_splits),
+                   _abi.attn_workspace_bytes(512, g.num_heads, g.head_dim, 4)) // 4 + 16
+        if self.ws.numel() < need:
+            self.ws = torch.zeros(need, dtype=torch.float32, device=self.device)
+
+    def set_suppress(self, mask):
+        """Ids that are never emitted (HF `suppress_tokens`; the synthetic streams use it to keep a random-init model inside the
+        token grammar).  Updated in place when possible: the mask's address is part of the captured graphs."""
+        mask = mask.to(self.device)
+        if self.suppress is not None and self.suppress.shape == mask.shape:
+            if self.suppress.data_ptr() != mask.data_ptr():
+                self.suppress.copy_(mask)
+                self.suppress_u8.copy_(mask)
+            return
+        self.suppress = mask.clone()
+        self.suppress_u8 = mask.to(torch.uint8).contiguous()
+        self._graphs.clear()
+        self._pf_graphs.clear()
 
     # ------------------------------------------------------------------ small helpers
     def _mark(self, name):
@@ -343,67 +476,100 @@ class StreamingEngine:
             logits = logits.masked_fill(self.suppress, float("-inf"))
         return logits
 
-    def prefill(self, new_ids, video_embeds, taps=None):
-        """Forward over the uncached ids (already uploaded as the tail of `cache.ids_dev`, positions in `cache.pos`).
-        With `use_graph`, one CUDA graph per (T, video-token layout, live buffer): the arena row and the kv length are
-        read from device memory, so the same graph serves every steady-state chunk."""
+    def _gen_key(self, gen):
+        # the seed is NOT part of the key: it lives in device memory (`rng_dev`), a new seed needs no new graph
+        return (gen.do_sample, float(gen.repetition_penalty), float(gen.temperature))
+
+    def _select_token(self, x_last, pending_last, gen, counters=None):
+        """Final norm + lm_head + token selection (`gen`) in ONE kernel pair: the chosen id lands in `tok_dev`.  `counters`:
+        the (kv_len, kv_after, next_pos) device scalars the launch advances (decode) -- scratch for the prefill."""
+        g = self.geo
+        x = x_last.reshape(-1)
+        if pending_last is not None:
+            x = x + pending_last.reshape(-1)
+        kv_len, kv_after, next_pos = counters if counters is not None else self._scratch_cnt.split(1)
+        _abi.lm_head_sample(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev, kv_len, kv_after, next_pos,
+                            seen=self.seen, repetition_penalty=gen.repetition_penalty, temperature=gen.temperature,
+                            do_sample=gen.do_sample, rng_state=self.rng_dev)
+        self.launches += 2
+
+    def prefill(self, new_ids, video_embeds, taps=None, gen: GenConfig = None):
+        """Forward over the uncached ids (already uploaded as the tail of `cache.ids_dev`, positions in `cache.pos`); leaves the
+        first token of the turn in `tok_dev` (selected by `gen` inside the lm_head kernel).
+        With `use_graph`, one CUDA graph per (token-count bucket, splits, live buffer, generation config): the arena row, the kv
+        length, the number of real tokens and the layout of the video placeholders are read from device memory, so the same
+        graph serves every chunk whose new-token count falls into the bucket; rows beyond the real count are padding (causal
+        attention: they come after every real row, their K/V rows lie beyond the live length and are overwritten by decode)."""
         c, g = self.cache, self.geo
+        gen = gen or self.gen
+        c.ensure_rotated()
         t, start = len(new_ids), c.seq_len
         if start + t > c.capacity:
             raise RuntimeError(f"sequence of {start + t} tokens exceeds the arena capacity {c.capacity}")
-        runs = ()
+        n_video = 0
         if video_embeds is not None:
-            ids_np = np.asarray(new_ids)
-            where = np.flatnonzero(ids_np == VIDEO_PAD)
-            if where.size != video_embeds.shape[0]:
-                raise ValueError(f"Video features and video tokens do not match: tokens: {where.size}, features {video_embeds.shape[0]}")
-            brk = np.flatnonzero(np.diff(where) != 1) + 1
-            runs = tuple((int(where[a]), int(b - a)) for a, b in zip(np.concatenate([[0], brk]), np.concatenate([brk, [where.size]])))
-        splits = self.prefill_splits or (1 if (-(-t // (128 // g.group))) * g.num_kv_heads >= 74 or start + t < 2048 or t > 512 else 2)
-        if not self.use_graph or taps is not None or t < 2 or t > self._pf_ids.numel():
-            logits = self._prefill_body(c.ids_dev[start:start + t], t, start, video_embeds, runs, splits, False, taps)
+            n_video = video_embeds.shape[0]
+            n_pad = int(np.count_nonzero(np.asarray(new_ids) == VIDEO_PAD))
+            if n_pad != n_video:
+                raise ValueError(f"Video features and video tokens do not match: tokens: {n_pad}, features {n_video}")
+        t_pad = min(-(-t // self.prefill_bucket) * self.prefill_bucket, c.capacity - start)
+        graphed = self.use_graph and taps is None and t >= 2 and t_pad <= self._pf_ids.numel() and n_video <= self._pf_video.shape[0]
+        if not graphed:
+            t_pad = t
+        splits = self.prefill_splits or (1 if (-(-t_pad // (128 // g.group))) * g.num_kv_heads >= 74 or start + t_pad < 2048 or t_pad > 512 else 2)
+        if not graphed:
+            self._prefill_body(c.ids_dev[start:start + t], t, t, start, video_embeds, n_video, splits, False, taps, gen)
         else:
             self._pf_ids[:t].copy_(c.ids_dev[start:start + t])
+            if t_pad > t:
+                self._pf_ids[t:t_pad].zero_()
+            self._pf_last.fill_(t - 1)
+            if n_video:
+                self._pf_video[:n_video].copy_(video_embeds)
             self.kv_len_dev.fill_(start)
-            self.kv_after_dev.fill_(start + t)
-            key = (t, runs, splits, c.cur, None if video_embeds is None else video_embeds.data_ptr())
+            self.kv_after_dev.fill_(start + t_pad)
+            key = (t_pad, splits, c.cur, n_video > 0, self._gen_key(gen))
+            n_cap = self._pf_video.shape[0] if n_video else 0     # baked into the graph: the static buffer's size, not this chunk's count
             entry = self._pf_graphs.get(key)
             if entry is None:
+                saved = (self.seen.clone(), self.rng_dev.clone())
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    self._prefill_body(self._pf_ids[:t], t, start, video_embeds, runs, splits, True, None)   # warm-up
+                    self._prefill_body(self._pf_ids[:t_pad], t_pad, t, start, self._pf_video, n_cap, splits, True, None, gen)   # warm-up
                 torch.cuda.current_stream().wait_stream(side)
+                self.seen.copy_(saved[0]); self.rng_dev.copy_(saved[1])
                 torch.cuda.synchronize()
                 before = self.launches
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
-                    out = self._prefill_body(self._pf_ids[:t], t, start, video_embeds, runs, splits, True, None)
-                entry = self._pf_graphs[key] = (gr, out, self.launches - before)
+                    self._prefill_body(self._pf_ids[:t_pad], t_pad, t, start, self._pf_video, n_cap, splits, True, None, gen)
+                entry = self._pf_graphs.put(key, (gr, self.launches - before))
                 self.launches = before
-            gr, logits, n_launch = entry
+            gr, n_launch = entry
             gr.replay()
             self.launches += n_launch
         c.seq_len = start + t
         c._seen_tokens += t
-        if taps is not None:
-            taps["logits"] = logits[0]
-        return logits
 
-    def _prefill_body(self, ids, t, start, video_embeds, runs, splits, dev_start, taps):
+    def _prefill_body(self, ids, t_pad, t, start, video_embeds, n_video, splits, dev_start, taps, gen):
         g = self.geo
-        x = F.embedding(ids, self.embed)
-        o = 0
-        for a, n in runs:
-            x[a:a + n] = video_embeds[o:o + n]
-            o += n
+        x = torch.empty(t_pad, g.hidden, dtype=torch.bfloat16, device=self.device)
+        _abi.embed_tokens(ids, t_pad, self.embed, video_embeds if n_video else None, n_video, x, self._pf_status, VIDEO_PAD)
+        self.launches += 1
         pending = None
         for li in range(g.num_layers):
-            x, pending = self._layer(x, pending, li, t, start, self.cache.capacity if dev_start else start + t, splits, taps, dev_start)
-        return self._logits(x[-1:].contiguous(), pending[-1:].contiguous())
+            x, pending = self._layer(x, pending, li, t_pad, start, self.cache.capacity if dev_start else start + t_pad, splits, taps, dev_start)
+        if dev_start:           # padded prefill: the last REAL row is named by a device scalar
+            x_last, p_last = x.index_select(0, self._pf_last), pending.index_select(0, self._pf_last)
+        else:
+            x_last, p_last = x[t - 1:t], pending[t - 1:t]
+        if taps is not None:
+            taps["logits"] = self._logits(x_last.contiguous(), p_last.contiguous())[0]
+        self._select_token(x_last, p_last, gen)
 
     # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
-    def _decode_body(self):
+    def _decode_body(self, gen: GenConfig = GREEDY):
         """One decode forward, every op a kernel of libsvlm_b200.so except the embedding row lookup: per layer
         norm+QKV GEMV -> rotate/append -> split-KV attention (+merge) -> o_proj GEMV + residual -> norm+gate/up GEMV
         with SwiGLU -> down GEMV + residual; then final norm + lm_head GEMV + argmax + counter update."""
@@ -437,13 +603,15 @@ class StreamingEngine:
                 _abi.gemv_bf16(L["wd"], act, part, 0)
                 x.add_(self._reduce(part))
         self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0) + ((2 if self._prefetch_gu_bytes else 1) if self._prefetch else 0))
-        _abi.lm_head_argmax(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
-                            self.kv_len_dev, self.kv_after_dev, c.next_pos)
+        _abi.lm_head_sample(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
+                            self.kv_len_dev, self.kv_after_dev, c.next_pos, seen=self.seen, repetition_penalty=gen.repetition_penalty,
+                            temperature=gen.temperature, do_sample=gen.do_sample, rng_state=self.rng_dev)
         self.launches += 2
 
-    def decode_step(self):
-        """Consumes `tok_dev`, appends its K/V, leaves the next greedy token in `tok_dev`."""
+    def decode_step(self, gen: GenConfig = None):
+        """Consumes `tok_dev`, appends its K/V, leaves the next token (selected by `gen`) in `tok_dev`."""
         c = self.cache
+        gen = gen or self.gen
         if c.seq_len + 1 > c.capacity:
             raise RuntimeError(f"arena capacity {c.capacity} exceeded during decode")
         # split count for the current cache length: ~2 key tiles per CTA keeps the serial TMA->UMMA->softmax chain short, at most
@@ -451,45 +619,61 @@ class StreamingEngine:
         n_tiles = (c.seq_len + 128) // 128
         self._splits_now = max(1, min(self.decode_splits, 148 // self.geo.num_kv_heads, -(-n_tiles // 2)))
         if self.use_graph:
-            gr = self._graphs.get((c.cur, self._splits_now))
+            key = (c.cur, self._splits_now, self._gen_key(gen))
+            gr = self._graphs.get(key)
             if gr is None:
                 # warm up once outside capture (cuBLAS workspaces, lazy kernel loading), then restore the state it advanced
-                saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone(), self.kv_after_dev.clone())
+                saved = (self.kv_len_dev.clone(), c.next_pos.clone(), self.tok_dev.clone(), self.kv_after_dev.clone(), self.seen.clone(),
+                         self.rng_dev.clone())
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
-                    self._decode_body()
+                    self._decode_body(gen)
                 torch.cuda.current_stream().wait_stream(s)
                 self.kv_len_dev.copy_(saved[0]); c.next_pos.copy_(saved[1]); self.tok_dev.copy_(saved[2]); self.kv_after_dev.copy_(saved[3])
+                self.seen.copy_(saved[4]); self.rng_dev.copy_(saved[5])
                 torch.cuda.synchronize()
                 before = self.launches
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
-                    self._decode_body()
+                    self._decode_body(gen)
                 self._graph_launches = self.launches - before
                 self.launches = before
-                self._graphs[(c.cur, self._splits_now)] = gr
+                self._graphs.put(key, gr)
             gr.replay()
             self.launches += self._graph_launches
         else:
-            self._decode_body()
+            self._decode_body(gen)
         c.seq_len += 1
         c._seen_tokens += 1
 
-    def generate(self, ids_full, pixels, grid, taps=None, forced=None):
-        """`model.generate` of the reference for one chunk: ViT + prefill + <= max_new_tokens greedy tokens.
+    def generate(self, ids_full, pixels, grid, taps=None, forced=None, gen: GenConfig = None, max_new_tokens=None, eos=IM_END):
+        """`model.generate` of the reference for one chunk: ViT + prefill + <= max_new_tokens tokens selected by `gen`
+        (default: the engine's own config; `GREEDY` is the parity mode, `REFERENCE_SAMPLING` the reference's).
         `forced` (teacher forcing, the reference's --gt_json idea, inference.py:231-239): token j of the chunk is
-        taken from this list instead of the argmax; the argmax is still recorded in `self.last_argmax`."""
+        taken from this list instead of the selected one; the selection is still recorded in `self.last_argmax`."""
         c = self.cache
+        gen = gen or self.gen
+        budget = self.max_new_tokens if max_new_tokens is None else int(max_new_tokens)
         input_len = len(ids_full)
         new_ids = ids_full[c.seq_len:]
+        if gen.repetition_penalty != 1.0:
+            # the penalty applies to every id of the sequence so far (`input_ids` of `_sample`); cache.ids_dev holds them
+            _abi.mark_seen(c.ids_dev, input_len, self.seen, clear_first=True)
+            self.launches += 1
+        if gen.do_sample:
+            # Philox key of this turn: the caller's seed, or the engine's own stream (base seed, turn counter); step word = 0
+            seed = gen.seed if gen.seed is not None else ((self.base_seed & 0xFFFFFFFF) << 32) | (self._turns & 0xFFFFFFFF)
+            self._rng_host[:] = torch.tensor(_abi.rng_words(seed), dtype=torch.int32)
+            self.rng_dev.copy_(self._rng_host, non_blocking=True)
+            self._turns += 1
         self._mark("vit_start")
         video = self.vision_forward(pixels, grid, taps) if pixels is not None else None
         if taps is not None and video is not None:
             taps["video_embeds"] = video
         self._mark("prefill_start")
-        logits = self.prefill(new_ids, video, taps)
-        self.tok_dev.copy_(torch.argmax(logits, dim=-1))
+        self.prefill(new_ids, video, taps, gen)
+        self._pf_status_pinned.copy_(self._pf_status, non_blocking=True)
         self._mark("decode_start")
         self.kv_len_dev.fill_(c.seq_len)
         self.kv_after_dev.fill_(c.seq_len + 1)
@@ -497,7 +681,7 @@ class StreamingEngine:
         n_fwd = 1
         self.last_argmax = []
         if forced is None and self.use_graph:
-            # Greedy loop with one step of look-ahead: the next decode step is enqueued BEFORE the host has seen the current
+            # Decode loop with one step of look-ahead: the next decode step is enqueued BEFORE the host has seen the current
             # token, so the GPU never idles on the device->host round trip.  The token copy is stream-ordered ahead of the
             # step that overwrites `tok_dev`.  If the token turns out to be <|im_end|>, the speculated step is rolled back:
             # its K/V row lies beyond the live length (never read), only the counters are restored.
@@ -508,24 +692,28 @@ class StreamingEngine:
                 pinned[slot].copy_(self.tok_dev, non_blocking=True)
                 ev = self._tok_events[slot]
                 ev.record()
-                will_be_last = len(seq) + 1 - input_len >= self.max_new_tokens     # the token being read fills the budget
+                will_be_last = len(seq) + 1 - input_len >= budget     # the token being read fills the budget
                 if not will_be_last and c.seq_len + 1 <= c.capacity:
-                    self.decode_step()
+                    self.decode_step(gen)
                     speculated = True
                 else:
                     speculated = False
                 ev.synchronize()
                 tok = int(pinned[slot][0])
+                if not self.last_argmax:
+                    self._check_chunk_status()
                 self.last_argmax.append(tok)
                 seq.append(tok)
-                if tok == IM_END or will_be_last:
+                if tok == eos or will_be_last:
                     if speculated:                      # undo the step that consumed the end token
                         c.seq_len -= 1
                         c._seen_tokens -= 1
                         c.next_pos.sub_(1)
+                        if gen.do_sample:
+                            self.rng_dev[2:3].sub_(1)
                     break
                 if not speculated:
-                    self.decode_step()                  # raises the capacity error
+                    self.decode_step(gen)               # raises the capacity error
                 n_fwd += 1
             self._mark("decode_end")
             return seq, n_fwd
@@ -533,17 +721,34 @@ class StreamingEngine:
             self.tok_pinned.copy_(self.tok_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             tok = int(self.tok_pinned[0])
+            if not self.last_argmax:
+                self._check_chunk_status()
             self.last_argmax.append(tok)
             if forced is not None and len(self.last_argmax) <= len(forced) and forced[len(self.last_argmax) - 1] != tok:
                 tok = int(forced[len(self.last_argmax) - 1])
                 self.tok_dev.fill_(tok)
+                if gen.repetition_penalty != 1.0:
+                    self.seen[tok] = 1
             seq.append(tok)
-            if tok == IM_END or len(seq) - input_len >= self.max_new_tokens:
+            if tok == eos or len(seq) - input_len >= budget:
                 break
-            self.decode_step()
+            self.decode_step(gen)
             n_fwd += 1
         self._mark("decode_end")
         return seq, n_fwd
+
+    def _check_chunk_status(self):
+        """Once per chunk, where the host has just synchronised on the first token anyway: the status words of the position
+        kernel (video run vs grid) and of the embedding splice (placeholder count, id range).  Their device->host copies were
+        enqueued ahead of the token copy, so nothing extra is waited for."""
+        self.cache.check_status()
+        st = int(self._pf_status_pinned[0])
+        if st:
+            self._pf_status.zero_()
+        if st & 8:
+            raise ValueError("Video features and video tokens do not match: more <|video_pad|> tokens than feature rows")
+        if st & 16:
+            raise ValueError("token id outside the vocabulary in the prompt")
 
     def load_state(self, state, seed=0):
         """Adopt the bookkeeping produced by `synthetic.fast_forward` and fill the arena with random K_raw / V for the
@@ -562,7 +767,9 @@ class StreamingEngine:
         c.set_video_grids(self.grids[:max(n_vid, 1)])
         self._grids_uploaded = None
         c.seq_len = n
-        c.compact([(0, 0, n)], self.prev_ids[:n])
+        c.compute_positions(self.prev_ids[:n])
+        c.compact([(0, 0, n)])
+        c.pos_upper = n
 
     # ------------------------------------------------------------------ session loop (inference.py:309-517)
     def begin_step(self, prompt_ids, grid, previous_text=""):
@@ -596,13 +803,9 @@ class StreamingEngine:
         moved = runs is not None and not (len(runs) == 1 and runs[0] == (0, 0, c.seq_len))
         if self.pos_mode == "append":
             if moved:
-                c.gather_positions(runs)
-                c.compact(runs)
+                c.compact(runs)                 # append mode: the positions travel with the rows (StreamingCache.compact)
                 self.launches += 1
-            self._pos_upper += len(ids) - c.seq_len + self.max_new_tokens
-            if self._pos_upper >= c.cos_table.shape[0]:
-                raise RuntimeError(f"append-mode positions would exceed the rotary table ({c.cos_table.shape[0]} rows): "
-                                   "construct the engine with a larger max_position")
+            c.reserve_positions(len(ids) - c.seq_len + self.max_new_tokens)
             c.append_positions(ids, c.seq_len, self.grids[-1])
             self._grids_uploaded = None
             self.launches += 1
@@ -618,12 +821,7 @@ class StreamingEngine:
         """Bookkeeping after generation (inference.py:457-517): close the turn, remember the ids, extend the history."""
         input_len = len(ids)
         if self.pos_mode == "append":
-            # the decode kernels rotate at `next_pos` without recording it; append mode needs the position of every cached row
-            # again at the next compaction: rows input_len .. seq_len-1 hold consecutive text positions ending at next_pos - 1
-            c = self.cache
-            n_dec = c.seq_len - input_len
-            if n_dec > 0:
-                c.pos[:, input_len:c.seq_len] = (c.next_pos - n_dec) + torch.arange(n_dec, dtype=torch.int32, device=self.device)
+            self.cache.record_decode_positions(input_len)
         if seq[-1] != IM_END:
             seq.append(IM_END)
         new_tokens = seq[input_len:]

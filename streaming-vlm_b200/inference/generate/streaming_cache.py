@@ -46,6 +46,9 @@ class _PlaneList:
         return c.arena[c.cur, self._plane, layer, :, :c.seq_len].unsqueeze(0)
 
     def __setitem__(self, layer, value):
+        """`cache.key_cache[i] = t` / `cache.value_cache[i] = t` with t `[1, H, n, D]`: rows 0..n-1 of that layer's plane are
+        replaced.  K_rot of the layer is no longer the rotation of its K_raw, and the positions recorded for the old rows
+        no longer describe the new ones: both are marked stale and re-derived before the next read (`ensure_rotated`)."""
         c = self._c
         n = value.shape[-2]
         if n > c.capacity:
@@ -53,13 +56,14 @@ class _PlaneList:
         c.arena[c.cur, self._plane, layer, :, :n].copy_(value.reshape(c.kv_heads, n, c.head_dim))
         if self._plane == K_RAW:
             c._rot_stale = True
+            c._pos_len = 0
         if layer == c.layers - 1 and self._plane == V_PLANE:
             c.seq_len = n
 
 
 class StreamingCache:
     def __init__(self, geo: Geometry = None, capacity: int = 8192, device="cuda", max_position: int = None,
-                 _distributed_cache_data=None):
+                 pos_mode: str = "shrink", _distributed_cache_data=None):
         if geo is None:
             raise RuntimeError("StreamingCache(geo=...) needs the model geometry to size its arena")
         if torch.device(device).type != "cuda":
@@ -95,7 +99,16 @@ class StreamingCache:
         self.position_ids_cache = []
         self.key_cache = _PlaneList(self, K_RAW)
         self.value_cache = _PlaneList(self, V_PLANE)
+        # K_rot bookkeeping: `_rot_stale` = some K_raw rows were written without their rotation (HF-style `update` before the
+        # positions were known, or `key_cache[i] = ...`); `_pos_len` = rows of `pos` that describe the current sequence
         self._rot_stale = False
+        self._pos_len = 0
+        if pos_mode not in ("append", "shrink"):
+            raise ValueError("pos_mode must be in ['append', 'shrink']")
+        self.pos_mode = pos_mode          # StreamingArgs.pos_mode of the session this cache belongs to (streaming_args.py:1-10)
+        self.pos_upper = 0                # append mode: host-side upper bound of the largest position handed out
+        self._status_pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._status_event = None
         self.compactions = 0
         self.decode_splits = max(1, min((self.capacity + 127) // 128, 296 // self.kv_heads))
         self._pending_start = 0
@@ -125,6 +138,7 @@ class StreamingCache:
         """Arena row at which layer `layer_idx` appends `t` new tokens.  All layers of one forward append at the
         same row; the sequence length advances once the last layer's append has been enqueued."""
         if layer_idx == 0:
+            self.ensure_rotated()
             self._pending_start = self.seq_len
             self._seen_tokens += t
         start = self._pending_start
@@ -135,23 +149,50 @@ class StreamingCache:
         return start
 
     def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
-        """Append raw K / V `[1, H, T, D]` for one layer; returns the `[1, H, S, D]` views (reference :30-74).
-        K_rot for the new rows is NOT produced here (the attention op does that, `svlm_qkv_rope_append`);
-        this method exists for callers that drive the cache the HF way."""
+        """Append raw K / V `[1, H, T, D]` for one layer; returns the `[1, H, S, D]` views of the RAW keys and the values, like
+        the reference (:30-74; rotation happens in its attention, language_forward.py:197).  For callers that drive the cache
+        the HF way.  The rotated copy of the new rows is written by the same append kernel the patched attention uses
+        (`svlm_qkv_rope_append`, append-only form) when the positions of those rows are already known (`compute_positions` /
+        `append_positions` ran for this forward); otherwise the cache is marked stale and `ensure_rotated` re-derives K_rot
+        as soon as they are."""
         t = key_states.shape[-2]
         start = self.layer_start(layer_idx, t)
-        self.arena[self.cur, K_RAW, layer_idx, :, start:start + t].copy_(key_states.reshape(self.kv_heads, t, self.head_dim))
-        self.arena[self.cur, V_PLANE, layer_idx, :, start:start + t].copy_(value_states.reshape(self.kv_heads, t, self.head_dim))
-        self._rot_stale = True
+        if self._pos_len >= start + t and not self._rot_stale:
+            k = key_states.reshape(self.kv_heads, t, self.head_dim).transpose(0, 1).reshape(t, -1).to(torch.bfloat16).contiguous()
+            v = value_states.reshape(self.kv_heads, t, self.head_dim).transpose(0, 1).reshape(t, -1).to(torch.bfloat16).contiguous()
+            _abi.qkv_rope_append(self.view, self.cur, layer_idx, None, k, v, t, 0, None, start, self.pos, self.cos_table, self.sin_table,
+                                 self.section)
+        else:
+            self.arena[self.cur, K_RAW, layer_idx, :, start:start + t].copy_(key_states.reshape(self.kv_heads, t, self.head_dim))
+            self.arena[self.cur, V_PLANE, layer_idx, :, start:start + t].copy_(value_states.reshape(self.kv_heads, t, self.head_dim))
+            self._rot_stale = True
         n = start + t
         return (self.arena[self.cur, K_RAW, layer_idx, :, :n].unsqueeze(0), self.arena[self.cur, V_PLANE, layer_idx, :, :n].unsqueeze(0))
 
+    def ensure_rotated(self):
+        """Honour `_rot_stale`: re-derive K_rot of every live row from K_raw at the positions in `self.pos` (one identity
+        compaction launch into the other buffer).  Raises if rows were replaced and no positions have been computed for them
+        since -- attention over keys rotated for a different sequence would be silently wrong."""
+        if not self._rot_stale:
+            return
+        n = self.seq_len
+        if n == 0:
+            self._rot_stale = False
+            return
+        if self._pos_len < n:
+            raise RuntimeError(f"StreamingCache: K_raw rows were written through update()/key_cache[i] = ... and no positions are known for "
+                               f"them ({self._pos_len} < {n} rows): call compute_positions(ids) (shrink mode) before the next attention")
+        self.compact([(0, 0, n)])
+
     # ------------------------------------------------------------------ B200 path
     def set_video_grids(self, grids):
-        """grids: iterable of (t, h, w) consumed from index 0 by `compute_positions`, as the reference's
-        ever-growing `streaming_args.video_grid_thw` is (inference.py:415)."""
-        g = torch.as_tensor(np.asarray(grids, dtype=np.int32).reshape(-1, 3))
-        self.grids = g.to(self.device)
+        """grids: iterable of (t, h, w) or an `[n, 3]` tensor, consumed from index 0 by `compute_positions`, as the reference's
+        ever-growing `streaming_args.video_grid_thw` is (inference.py:415).  A CUDA tensor is used as is (no host round trip)."""
+        if isinstance(grids, torch.Tensor):
+            g = grids.reshape(-1, 3).to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            g = torch.as_tensor(np.asarray(grids, dtype=np.int32).reshape(-1, 3)).to(self.device)
+        self.grids = g
         self.n_grids = g.shape[0]
 
     def upload_ids(self, ids) -> int:
@@ -169,12 +210,42 @@ class StreamingCache:
         self.ids_dev[:n].copy_(self.ids_pinned[:n], non_blocking=True)
         return n
 
-    def compute_positions(self, ids) -> int:
-        """Contiguous mRoPE positions of `ids` into `self.pos[:, :n]`; `self.next_pos` = max + 1."""
+    def compute_positions(self, ids, all_text: bool = False) -> int:
+        """Contiguous mRoPE positions of `ids` into `self.pos[:, :n]`; `self.next_pos` = max + 1.  `all_text`
+        (`StreamingArgs.all_text`, model_forward.py:6-28 `get_1d_rope_index`): every token advances all three axes by one."""
         n = self.upload_ids(ids)
         _abi.mrope_positions(self.ids_dev, n, self.grids, self.n_grids, self.pos, self.next_pos, self.status,
-                             self.spatial_merge, self.t_step, TOKEN_IDS["<|video_pad|>"])
+                             self.spatial_merge, self.t_step, -1 if all_text else TOKEN_IDS["<|video_pad|>"])
+        self._note_status()
+        self._pos_len = n
+        if self._rot_stale and n >= self.seq_len:
+            self.ensure_rotated()
         return n
+
+    def _note_status(self):
+        """Start the read-back of the position kernel's status word; `check_status` (called where the host synchronises
+        anyway, after the first token of a turn) raises on a video run that disagrees with its grid."""
+        self._status_pinned.copy_(self.status, non_blocking=True)
+        if self._status_event is None:
+            self._status_event = torch.cuda.Event()
+        self._status_event.record()
+
+    def check_status(self):
+        if self._status_event is None:
+            return
+        self._status_event.synchronize()
+        st = int(self._status_pinned[0])
+        if st & 1:
+            raise ValueError("a run of <|video_pad|> tokens does not match its (t, h, w) grid (t * h * w / merge^2 tokens expected)")
+        if st & 2:
+            raise ValueError("more video runs in the ids than grids in video_grid_thw")
+
+    def reserve_positions(self, n: int):
+        """append mode: `n` more positions are about to be handed out; the rotary tables must cover them."""
+        self.pos_upper += int(n)
+        if self.pos_upper >= self.cos_table.shape[0]:
+            raise RuntimeError(f"append-mode positions would exceed the rotary table ({self.cos_table.shape[0]} rows): "
+                               "construct the cache / engine with a larger max_position")
 
     # -- append position mode (reference: model_forward.py:112-153 + language_forward.py:184-188) -----------------
     def gather_positions(self, runs):
@@ -183,42 +254,78 @@ class StreamingCache:
         n = sum(r[2] for r in runs)
         self.pos[:, :n] = torch.cat([self.pos[:, s_:s_ + l] for s_, _, l in runs], dim=1)
 
-    def append_positions(self, ids, start: int, grid) -> int:
+    def append_positions(self, ids, start: int, grid, all_text: bool = False) -> int:
         """Positions of the uncached ids `ids[start:]` only: `get_rope_index` over the new ids with THIS chunk's grid, shifted by
-        last_cache_position + 1 (= `next_pos`, which the decode steps keep advancing); nothing is recomputed for the cache."""
+        last_cache_position + 1 (= `next_pos`, which the decode steps keep advancing); nothing is recomputed for the cache.
+        `grid`: (t, h, w), an `[n, 3]` tensor of the grids of this call, or None (no video among the new ids)."""
         n = self.upload_ids(ids)
+        return self._append_positions_uploaded(start, n, grid, all_text)
+
+    def append_new_positions(self, new_ids, grid, all_text: bool = False) -> int:
+        """Same for callers that only hold the NEW ids (the reference's append-mode `model_forward` sees the ids sliced to the
+        uncached suffix, model_forward.py:112-153): they are placed behind the cached rows."""
+        start = self.seq_len
+        new = new_ids.reshape(-1) if isinstance(new_ids, torch.Tensor) else torch.from_numpy(as_host_ids(new_ids))
+        n = start + new.numel()
+        if n > self.capacity:
+            raise RuntimeError(f"sequence of {n} tokens exceeds the arena capacity {self.capacity}")
+        self.ids_dev[start:n].copy_(new.to(torch.int64), non_blocking=True)
+        return self._append_positions_uploaded(start, n, grid, all_text)
+
+    def _append_positions_uploaded(self, start, n, grid, all_text):
         n_new = n - start
         offset = self.next_pos.clone()
         if start == 0:
             offset.zero_()
-        self.set_video_grids([grid])
+        if grid is not None:
+            self.set_video_grids(grid if isinstance(grid, torch.Tensor) else [grid])
         if not hasattr(self, "_pos_rel"):
             self._pos_rel = torch.zeros_like(self.pos)
         _abi.mrope_positions(self.ids_dev[start:], n_new, self.grids, self.n_grids, self._pos_rel, self.next_pos, self.status,
-                             self.spatial_merge, self.t_step, TOKEN_IDS["<|video_pad|>"])
+                             self.spatial_merge, self.t_step, -1 if all_text else TOKEN_IDS["<|video_pad|>"])
+        self._note_status()
         self.pos[:, start:n] = self._pos_rel[:, :n_new] + offset
         self.next_pos += offset
+        self._pos_len = n
         return n
 
+    def record_decode_positions(self, first_row: int):
+        """append mode: the decode kernels rotate at `next_pos` without recording it; the position of every cached row is needed
+        again at the next compaction.  Rows first_row .. seq_len-1 hold consecutive text positions ending at next_pos - 1."""
+        n_dec = self.seq_len - first_row
+        if n_dec > 0:
+            self.pos[:, first_row:self.seq_len] = (self.next_pos - n_dec) + torch.arange(n_dec, dtype=torch.int32, device=self.device)
+            self._pos_len = max(self._pos_len, self.seq_len)
+
     def compact(self, runs, new_ids=None):
-        """Gather `runs` = [(src, dst, len)] from the live buffer into the other one, re-rotating K at the
-        positions of `new_ids` (the pruned sequence; omitted = positions already in `self.pos`)."""
-        if new_ids is not None:
-            self.compute_positions(new_ids)
+        """Gather `runs` = [(src, dst, len)] from the live buffer into the other one, re-rotating K.  Shrink mode: at the
+        contiguous positions of `new_ids` (the pruned sequence; omitted = positions already in `self.pos`).  Append mode: every
+        retained token keeps its position (gathered with the same runs); `new_ids` only refreshes the device copy of the ids."""
+        runs = [tuple(int(x) for x in r) for r in runs]
+        if len(runs) > _abi.MAX_RUNS:
+            raise RuntimeError(f"gather has {len(runs)} runs; SVLM_MAX_RUNS is {_abi.MAX_RUNS} (the eviction policy produces <= 8)")
         n = sum(r[2] for r in runs)
-        for lo in range(0, max(len(runs), 1), _abi.MAX_RUNS):   # > MAX_RUNS runs: several launches, same buffers
-            part = runs[lo:lo + _abi.MAX_RUNS]
-            if not part:
-                break
-            if lo > 0:
-                raise RuntimeError(f"gather has {len(runs)} runs; SVLM_MAX_RUNS is {_abi.MAX_RUNS}")
-            _abi.kv_compact_rope(self.view, self.cur, part, self.pos, self.cos_table, self.sin_table, self.section)
+        if self.pos_mode == "append":
+            if new_ids is not None:
+                self.upload_ids(new_ids)
+            if not (len(runs) == 1 and runs[0][:2] == (0, 0)):
+                self.gather_positions(runs)
+            self._pos_len = n
+        elif new_ids is not None:
+            stale, self._rot_stale = self._rot_stale, False      # this compaction re-derives K_rot; no separate refresh first
+            self.compute_positions(new_ids)
+            self._rot_stale = stale
+        if self._pos_len < n:
+            raise RuntimeError(f"compact: positions are known for {self._pos_len} rows, the gather keeps {n}")
+        if runs:
+            _abi.kv_compact_rope(self.view, self.cur, runs, self.pos, self.cos_table, self.sin_table, self.section)
         self.cur ^= 1
         self.seq_len = n
         self._rot_stale = False
         self.compactions += 1
 
     def planes(self, layer):
+        self.ensure_rotated()
         b = self.arena[self.cur]
         n = self.seq_len
         return b[K_RAW, layer, :, :n], b[K_ROT, layer, :, :n], b[V_PLANE, layer, :, :n]

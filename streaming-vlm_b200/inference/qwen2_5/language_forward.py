@@ -1,4 +1,4 @@
-"""LLM forwards bound onto an HF Qwen2.5-VL text model (shrink position mode).
+"""LLM forwards bound onto an HF Qwen2.5-VL text model (both position modes of `StreamingArgs`).
 
 Patch points of the reference (`qwen2_5/language_forward.py`): attention :143-260, decoder layer :262-305,
 language model :395-516.  The attention keeps the reference's order -- project, cache the RAW keys, rotate
@@ -22,8 +22,8 @@ def streaming_text_flash_attn_forward(self, hidden_states, attention_mask=None, 
     cache = past_key_value if past_key_value is not None else past_key_values
     if output_attentions:
         raise RuntimeError("output_attentions=True is not available on the svlm CUDA path (no eager fallback)")
-    if streaming_args is None or streaming_args.pos_mode != "shrink":
-        raise RuntimeError("the svlm CUDA path implements pos_mode='shrink' (contiguous RoPE) only")
+    if streaming_args is None:
+        raise RuntimeError("streaming_args is required on the svlm CUDA path")
     if not isinstance(cache, StreamingCache):
         raise RuntimeError("past_key_values must be a streaming_vlm_b200 StreamingCache")
     bsz, q_len, _ = hidden_states.size()

@@ -2,9 +2,8 @@
 
 Same fields and meaning as the reference's `inference/streaming_args.py:1-10`
 (`pos_mode`, `all_text`, `input_ids`, `video_grid_thw`, `second_per_grid_ts`; append mode
-adds `last_cache_position`, `qwen2_5/model_forward.py:153`).  Only `pos_mode="shrink"` is on
-the B200 hot path; "append" is accepted and stored so callers can construct the object,
-but the CUDA path raises if asked to run it.
+adds `last_cache_position`, `qwen2_5/model_forward.py:153`).  Both position modes run on the
+B200 path (patched forwards and the session-runner fast path behind `generate`).
 """
 
 

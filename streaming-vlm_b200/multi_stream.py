@@ -93,9 +93,14 @@ class MultiStreamEngine:
         self.launches += (e0.launches - before) + g.num_layers * (2 + (1 if splits > 1 else 0))
         e0.launches = before
 
-    def decode_step(self):
-        """Every ACTIVE stream consumes its token in `self.tok`, appends its K/V and leaves its next greedy token there."""
+    def decode_step(self, done=None):
+        """Every ACTIVE stream consumes its token in `self.tok`, appends its K/V and leaves its next greedy token there.
+        `done[b]`: stream b finished its turn (its counters do not advance).  Like the single-stream engine, a stream that
+        would append beyond its arena raises instead of dropping the row."""
         caches = [e.cache for e in self.engines]
+        for b, c in enumerate(caches):
+            if (done is None or not done[b]) and c.seq_len + 1 > c.capacity:
+                raise RuntimeError(f"stream {b}: arena capacity {c.capacity} exceeded during decode")
         n_tiles = max(c.seq_len for c in caches) // 128 + 1
         splits = max(1, min(self.max_splits, -(-n_tiles // 3)))
         key = (tuple(c.cur for c in caches), splits)
@@ -249,8 +254,7 @@ class MultiStreamEngine:
             for b, e in enumerate(engines):
                 c = e.cache
                 video = e.vision_forward(pixels[b], grid) if pixels[b] is not None else None
-                logits = e.prefill(ids_all[b][c.seq_len:], video)
-                e.tok_dev.copy_(torch.argmax(logits, dim=-1))
+                e.prefill(ids_all[b][c.seq_len:], video)            # leaves the stream's first token in e.tok_dev (= self.tok[b])
                 e.kv_len_dev.fill_(c.seq_len)
                 e.kv_after_dev.fill_(c.seq_len + 1)
         seqs = [list(ids) for ids in ids_all]
@@ -280,7 +284,7 @@ class MultiStreamEngine:
                 for b in range(B):
                     self._active_pinned[b] = 0 if done[b] else 1
                 self.active.copy_(self._active_pinned, non_blocking=True)
-            self.decode_step()
+            self.decode_step(done)
             n_fwd += 1
             for b, e in enumerate(engines):
                 if not done[b]:

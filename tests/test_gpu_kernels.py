@@ -627,3 +627,60 @@ def test_torch_custom_ops_layer(abi):
     assert torch.equal(torch.ops.svlm.frames_resize_bicubic(fr, 28, 56), abi.frames_resize_bicubic(fr, 28, 56))
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.svlm.swiglu(gu.cpu())              # no CPU kernel is registered: there is no fallback
+
+
+# ------------------------------------------------------------------------------------------------ embed + video splice
+def test_embed_tokens_equals_embedding_plus_masked_scatter(abi):
+    """svlm_embed_tokens == F.embedding followed by the reference's masked_scatter of the video embeddings
+    (qwen2_5/model_forward.py:58, 87-93), for scattered and contiguous placeholder layouts; the status word flags a placeholder
+    count above the number of feature rows and ids outside the vocabulary."""
+    g = torch.Generator().manual_seed(11)
+    vocab, hidden, vid = 5000, 512, 4999
+    emb = torch.randn(vocab, hidden, generator=g).to(torch.bfloat16)
+    for layout in ("block", "scattered", "none"):
+        ids = torch.randint(0, vocab - 1, (301,), generator=g)
+        if layout == "block":
+            ids[20:276] = vid
+        elif layout == "scattered":
+            ids[torch.randperm(301, generator=g)[:77]] = vid
+        n_vid = int((ids == vid).sum())
+        video = torch.randn(max(n_vid, 1), hidden, generator=g).to(torch.bfloat16)
+        want = torch.nn.functional.embedding(ids, emb)
+        if n_vid:
+            mask = (ids == vid)[:, None].expand_as(want)
+            want = want.masked_scatter(mask, video[:n_vid])
+        out = torch.empty(301, hidden, dtype=torch.bfloat16, device=DEV)
+        status = torch.zeros(1, dtype=torch.int32, device=DEV)
+        abi.embed_tokens(ids.to(DEV), 301, emb.to(DEV), video.to(DEV) if n_vid else None, n_vid, out, status, vid)
+        assert torch.equal(bits(out.cpu()), bits(want)), layout
+        assert int(status) == 0
+    # more placeholders than feature rows -> bit 8; an id beyond the vocabulary -> bit 16
+    ids = torch.tensor([1, vid, vid, vid, 2], dtype=torch.long)
+    out = torch.empty(5, hidden, dtype=torch.bfloat16, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    abi.embed_tokens(ids.to(DEV), 5, emb.to(DEV), torch.zeros(2, hidden, dtype=torch.bfloat16, device=DEV), 2, out, status, vid)
+    assert int(status) & 8
+    status.zero_()
+    abi.embed_tokens(torch.tensor([1, vocab + 5], device=DEV), 2, emb.to(DEV), None, 0, out, status, vid)
+    assert int(status) & 16
+
+
+def test_qkv_rope_append_without_queries(abi, tables):
+    """q_heads = 0: the append-only form `StreamingCache.update` uses -- K_raw / K_rot / V rows, bit-exact vs the oracle's mRoPE."""
+    L, H, cap, t, start = 2, 2, 256, 37, 50
+    _, dev, view = make_arena(abi, L, H, cap, fill=False)
+    g = torch.Generator().manual_seed(3)
+    k = (torch.randn(t, H * 128, generator=g) * 0.5).to(torch.bfloat16)
+    v = (torch.randn(t, H * 128, generator=g) * 0.5).to(torch.bfloat16)
+    pos = torch.zeros(3, cap, dtype=torch.int32)
+    pos[:, start:start + t] = torch.randint(0, 4000, (3, t), generator=g, dtype=torch.int32)
+    tc, ts = tables
+    abi.qkv_rope_append(view, 0, 1, None, k.to(DEV), v.to(DEV), t, 0, None, start, pos.to(DEV), tc.to(DEV), ts.to(DEV), SECTION)
+    got = dev.cpu()
+    kk = k.view(t, H, 128).transpose(0, 1)
+    cos, sin = cos_sin_at(tables, pos[:, start:start + t])
+    _, want_rot = o_pos.apply_mrope(kk[None, :1, :1], kk[None], cos, sin, SECTION)
+    assert torch.equal(bits(got[0, 0, 1, :, start:start + t]), bits(kk))
+    assert torch.equal(bits(got[0, 1, 1, :, start:start + t]), bits(want_rot[0]))
+    assert torch.equal(bits(got[0, 2, 1, :, start:start + t]), bits(v.view(t, H, 128).transpose(0, 1)))
+    assert got[0, :, 0].abs().sum() == 0 and got[0, :, 1, :, :start].abs().sum() == 0          # nothing else was touched

@@ -8,6 +8,7 @@ import torch
 from oracle.model import Session
 from streaming_vlm_b200 import synthetic
 from streaming_vlm_b200.config import TINY
+from tests.parity_log import record
 from tests.stream_sim import rle
 
 pytestmark = pytest.mark.gpu
@@ -59,7 +60,8 @@ def test_three_streams_small_windows(batch_prefill):
     mism, total, multi = _run(3, 12, 112, 112, 4, 4, 16, 24, batch_prefill=batch_prefill)
     assert all(e.cache.compactions >= 6 for e in multi.engines)
     assert len({tuple(e.prev_ids.tolist()) for e in multi.engines}) == 3          # the streams really differ
-    assert mism <= max(2, total // 20), (mism, total)
+    record("multistream", batch_prefill=batch_prefill, greedy_mismatches=mism, greedy_tokens=total)
+    assert mism <= max(1, total // 100), (mism, total)
 
 
 def test_two_streams_eager_equals_graph():

@@ -16,6 +16,7 @@ from oracle import positions as o_pos
 from oracle.model import Session
 from streaming_vlm_b200 import synthetic
 from streaming_vlm_b200.config import TINY
+from tests.parity_log import record
 from tests.stream_sim import rle
 
 pytestmark = pytest.mark.gpu
@@ -34,6 +35,7 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
                              text_round=text_round, text_sink=sink, text_sliding_window=sliding, suppress=suppress, pos_mode=pos_mode)
     n_vis = (height // 28) * (width // 28)
     mismatches, total, prev_cache_len = 0, 0, 0
+    ve_worst = 0.0
     for i in range(n_chunks):
         px, grid = synthetic.patchify(synthetic.frames(i, height, width), geo)
         prompt = synthetic.round_prompt(i, n_vis, n_prev)
@@ -72,7 +74,9 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
             _, ref_rot = o_pos.apply_mrope(kr[None, :1, :1], kr[None], cos, sin, geo.mrope_section)
             assert torch.equal(k_rot[:, :n].cpu().view(torch.int16), ref_rot[0].view(torch.int16)), f"chunk {i}: K_rot"
             # floating point rows
-            torch.testing.assert_close(taps_g["video_embeds"].float().cpu(), taps_o["video_embeds"].float(), rtol=5e-2, atol=5e-2)
+            ve = (taps_g["video_embeds"].float().cpu() - taps_o["video_embeds"].float()).abs().max().item()
+            ve_worst = max(ve_worst, ve / taps_o["video_embeds"].float().abs().max().item())
+            torch.testing.assert_close(taps_g["video_embeds"].float().cpu(), taps_o["video_embeds"].float(), rtol=3e-2, atol=3e-2)
             for li in range(geo.num_layers):
                 torch.testing.assert_close(taps_g["attn_out"][li].float().cpu(), taps_o["attn_out"][li].float(), **ATTN_TOL)
             lg, lo = taps_g["logits"].cpu(), taps_o["logits"]
@@ -85,6 +89,8 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
                 mismatches += 1
                 lo = ro["step_logits"][j]
                 assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]}"
+    record("tiny_stream", chunks=n_chunks, frame=f"{height}x{width}", pos_mode=pos_mode, greedy_mismatches=mismatches, greedy_tokens=total,
+           video_embeds_max_rel=ve_worst)
     return mismatches, total, engine, oracle
 
 
@@ -93,14 +99,14 @@ def test_tiny_stream_small_windows():
     eviction branch (move, user block drop, previous-text trim) is exercised within 20 chunks."""
     mism, total, engine, _ = _run(20, 112, 112, 4, 4, 16, 24, 6)
     assert engine.cache.compactions >= 14
-    assert mism <= max(2, total // 20), (mism, total)
+    assert mism <= max(1, total // 100), (mism, total)       # teacher-forced near-ties only (each one checked against the oracle's margin)
 
 
 def test_tiny_stream_config1():
     """BASELINE.json configs[0]: 64 frames of 448x448 = 32 chunks, defaults 16/16/512/512."""
     mism, total, engine, oracle = _run(32, 448, 448, 16, 16, 512, 512, 24, check_every=4)
     assert engine.cache.compactions >= 15
-    assert mism <= max(2, total // 20), (mism, total)
+    assert mism <= max(1, total // 100), (mism, total)
 
 
 def test_tiny_stream_append_position_mode():
@@ -110,7 +116,7 @@ def test_tiny_stream_append_position_mode():
     assert engine.cache.compactions >= 14
     assert int(engine.cache.next_pos) == oracle.pos_state["last_cache_position"] + 1
     assert int(engine.cache.next_pos) > 2 * engine.cache.seq_len          # positions really outgrew the cache
-    assert mism <= max(2, total // 20), (mism, total)
+    assert mism <= max(1, total // 100), (mism, total)
 
 
 def test_lookahead_decode_equals_plain_loop():
@@ -124,7 +130,8 @@ def test_lookahead_decode_equals_plain_loop():
     suppress[torch.tensor([IM_END, 1000, 1001, 1002])] = False
     for pos_mode in ("shrink", "append"):
         engines = [StreamingEngine({k: v.clone() for k, v in w_cpu.items()}, geo, capacity=4096, window_size=4, text_round=4, text_sink=16,
-                                   text_sliding_window=24, suppress=suppress, use_graph=ug, pos_mode=pos_mode) for ug in (True, False)]
+                                   text_sliding_window=24, suppress=suppress, use_graph=ug, pos_mode=pos_mode, prefill_bucket=1)
+                   for ug in (True, False)]         # prefill_bucket=1: same GEMM shapes on both sides, so the arenas can be compared bit for bit
         early = 0
         for i in range(14):
             px, grid = synthetic.patchify(synthetic.frames(i, 112, 112), geo)
@@ -138,3 +145,37 @@ def test_lookahead_decode_equals_plain_loop():
         n = engines[0].cache.seq_len
         a, b = (e.cache.arena[e.cache.cur, :, :, :, :n] for e in engines)
         assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"{pos_mode}: arenas differ"
+
+
+def test_padded_prefill_graphs_and_variable_turns_stay_bounded():
+    """Chunk-prefill graphs are keyed on a token-count BUCKET (padded tail rows, device-side true length) and both graph caches are
+    LRU-bounded: a stream whose turns end after 1..20 tokens and whose prompts vary in length (1..9 time tokens) must (a) give
+    the same stream as exact-length prefills, (b) keep the number of captured graphs and the allocated HBM flat."""
+    from streaming_vlm_b200.engine import IM_END, StreamingEngine
+    geo = TINY
+    w_cpu = synthetic.random_weights(geo, seed=0)
+    suppress = torch.ones(geo.vocab, dtype=torch.bool)
+    suppress[torch.tensor([IM_END] + list(range(1000, 1012)))] = False          # 13 ids: turns end early at random points
+    mk = lambda bucket, limit: StreamingEngine({k: v.clone() for k, v in w_cpu.items()}, geo, capacity=4096, window_size=4, text_round=4,
+                                               text_sink=16, text_sliding_window=24, suppress=suppress, prefill_bucket=bucket, max_graphs=limit)
+    padded, exact = mk(8, 6), mk(1, 64)
+    lens, mem, worst = set(), [], 0.0
+    for i in range(60):
+        px, grid = synthetic.patchify(synthetic.frames(i, 112, 112), geo)
+        prompt = synthetic.round_prompt(i, 16, 6, time_tokens=1 + (i * 5) % 9)
+        ra = padded.step(prompt, px.to("cuda"), grid)
+        rb = exact.step(prompt, px.to("cuda"), grid, forced=ra["new_tokens"])
+        assert ra["ids"] == rb["ids"] and ra["cache_len"] == rb["cache_len"] and ra["runs"] == rb["runs"], f"chunk {i}"
+        lens.add(len(ra["new_tokens"]))
+        n = padded.cache.seq_len
+        a, b = (e.cache.arena[e.cache.cur, :, :, :, :n].float() for e in (padded, exact))
+        worst = max(worst, ((a - b).abs().max() / b.abs().max()).item())
+        # the exact engine's own selections: identical except at near-ties of the two GEMM shapes
+        mem.append(torch.cuda.memory_allocated())
+    record("padded_prefill_variable_turns", turn_lengths=sorted(lens), prefill_graphs=len(padded._pf_graphs), decode_graphs=len(padded._graphs),
+           prefill_graph_evictions=padded._pf_graphs.evictions, exact_prefill_graphs=len(exact._pf_graphs), arena_max_rel_diff=worst)
+    assert len(lens) >= 5, lens                                            # the turns really varied
+    assert worst < 2e-2, worst                                             # same K/V rows up to the GEMM-shape rounding
+    assert len(padded._pf_graphs) <= 6 and len(padded._graphs) <= 6
+    assert len(exact._pf_graphs) > len(padded._pf_graphs) or padded._pf_graphs.evictions == 0
+    assert max(mem[30:]) - min(mem[30:]) < (64 << 20), "allocated HBM keeps moving with bounded graph caches"
