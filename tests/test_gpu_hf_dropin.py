@@ -16,7 +16,7 @@ import torch
 from oracle.model import Session
 from streaming_vlm_b200 import synthetic
 from streaming_vlm_b200.config import from_hf_config
-from tests.parity_log import record
+from tests.parity_log import MAX_NEAR_TIE_FRACTION, near_tie, record
 
 pytestmark = pytest.mark.gpu
 
@@ -97,7 +97,7 @@ def _drive(family, pos_mode, fast, monkeypatch, n_chunks=8, repetition_penalty=1
             if tg != to:
                 mism += 1
                 lo = ro["step_logits"][j]
-                assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} token {j}: selected {tg}, oracle {to}, oracle margin {lo[to] - lo[tg]}"
+                assert near_tie(lo, tg, to), f"chunk {i} token {j}: selected {tg}, oracle {to}, oracle margin {lo[to] - lo[tg]} top {lo[to]}"
     if pos_mode == "append":
         assert args.last_cache_position == oracle.pos_state["last_cache_position"]
         assert int(past.next_pos) == oracle.pos_state["last_cache_position"] + 1
@@ -112,7 +112,7 @@ def test_patched_qwen2_5_matches_oracle(fast, pos_mode, monkeypatch):
     record("hf_dropin", path="fast" if fast else "eager", pos_mode=pos_mode, mismatches=mism, tokens=total)
     assert cache.compactions >= 4
     assert (getattr(model, "_svlm_engine", None) is not None) == fast          # the fast path really ran on the session runner
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
     if fast:
         eng = model._svlm_engine
         # one copy of the weights: the HF modules' parameters are views of the engine's fused tensors
@@ -129,7 +129,7 @@ def test_patched_qwen2_5_cache_created_by_generate(monkeypatch):
     mism, total, model, cache = _drive("qwen2_5", "shrink", True, monkeypatch, n_chunks=5, pass_cache=False)
     record("hf_dropin_cache_created", mismatches=mism, tokens=total)
     assert cache is model._svlm_engine.cache and cache.compactions >= 2
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_patched_qwen2_5_repetition_penalty_matches_oracle(monkeypatch):
@@ -138,7 +138,7 @@ def test_patched_qwen2_5_repetition_penalty_matches_oracle(monkeypatch):
     for fast in (True, False):
         mism, total, _, _ = _drive("qwen2_5", "shrink", fast, monkeypatch, n_chunks=6, repetition_penalty=1.05)
         record("hf_dropin_penalty", path="fast" if fast else "eager", mismatches=mism, tokens=total)
-        assert mism <= max(1, total // 100), (mism, total)
+        assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_patched_qwen2_matches_oracle(monkeypatch):
@@ -146,7 +146,7 @@ def test_patched_qwen2_matches_oracle(monkeypatch):
     mism, total, model, cache = _drive("qwen2", "shrink", True, monkeypatch, n_chunks=6)
     record("hf_dropin_qwen2", mismatches=mism, tokens=total)
     assert cache.compactions >= 3 and getattr(model, "_svlm_engine", None) is None
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_reference_generation_config_runs_on_the_fast_path(monkeypatch):

@@ -8,7 +8,7 @@ import torch
 from oracle.model import Session
 from streaming_vlm_b200 import synthetic
 from streaming_vlm_b200.config import TINY
-from tests.parity_log import record
+from tests.parity_log import MAX_NEAR_TIE_FRACTION, near_tie, record
 from tests.stream_sim import rle
 
 pytestmark = pytest.mark.gpu
@@ -50,7 +50,7 @@ def _run(n_streams, n_chunks, height, width, window, text_round, sink, sliding, 
                 if tg != to:
                     mismatches += 1
                     lo = ro["step_logits"][j]
-                    assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} stream {b} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]}"
+                    assert near_tie(lo, tg, to), f"chunk {i} stream {b} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]} top {lo[to]}"
     return mismatches, total, multi
 
 
@@ -61,7 +61,7 @@ def test_three_streams_small_windows(batch_prefill):
     assert all(e.cache.compactions >= 6 for e in multi.engines)
     assert len({tuple(e.prev_ids.tolist()) for e in multi.engines}) == 3          # the streams really differ
     record("multistream", batch_prefill=batch_prefill, greedy_mismatches=mism, greedy_tokens=total)
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_two_streams_eager_equals_graph():

@@ -16,7 +16,7 @@ from oracle import positions as o_pos
 from oracle.model import Session
 from streaming_vlm_b200 import synthetic
 from streaming_vlm_b200.config import TINY
-from tests.parity_log import record
+from tests.parity_log import MAX_NEAR_TIE_FRACTION, near_tie, record
 from tests.stream_sim import rle
 
 pytestmark = pytest.mark.gpu
@@ -88,7 +88,7 @@ def _run(n_chunks, height, width, window, text_round, sink, sliding, n_prev, che
             if tg != to:
                 mismatches += 1
                 lo = ro["step_logits"][j]
-                assert lo[to] - lo[tg] < LOGIT_TOL, f"chunk {i} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]}"
+                assert near_tie(lo, tg, to), f"chunk {i} token {j}: engine {tg} oracle {to} margin {lo[to] - lo[tg]} top {lo[to]}"
     record("tiny_stream", chunks=n_chunks, frame=f"{height}x{width}", pos_mode=pos_mode, greedy_mismatches=mismatches, greedy_tokens=total,
            video_embeds_max_rel=ve_worst)
     return mismatches, total, engine, oracle
@@ -99,14 +99,14 @@ def test_tiny_stream_small_windows():
     eviction branch (move, user block drop, previous-text trim) is exercised within 20 chunks."""
     mism, total, engine, _ = _run(20, 112, 112, 4, 4, 16, 24, 6)
     assert engine.cache.compactions >= 14
-    assert mism <= max(1, total // 100), (mism, total)       # teacher-forced near-ties only (each one checked against the oracle's margin)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)       # near-ties only: each one was checked against the oracle's margin
 
 
 def test_tiny_stream_config1():
     """BASELINE.json configs[0]: 64 frames of 448x448 = 32 chunks, defaults 16/16/512/512."""
     mism, total, engine, oracle = _run(32, 448, 448, 16, 16, 512, 512, 24, check_every=4)
     assert engine.cache.compactions >= 15
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_tiny_stream_append_position_mode():
@@ -116,7 +116,7 @@ def test_tiny_stream_append_position_mode():
     assert engine.cache.compactions >= 14
     assert int(engine.cache.next_pos) == oracle.pos_state["last_cache_position"] + 1
     assert int(engine.cache.next_pos) > 2 * engine.cache.seq_len          # positions really outgrew the cache
-    assert mism <= max(1, total // 100), (mism, total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
 def test_lookahead_decode_equals_plain_loop():
