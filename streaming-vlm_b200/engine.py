@@ -317,8 +317,8 @@ class StreamingEngine:
         g = self.geo
         if (cache.layers, cache.kv_heads, cache.head_dim) != (g.num_layers, g.num_kv_heads, g.head_dim):
             raise RuntimeError("StreamingCache geometry does not match the model")
-        if cache.device != self.device:
-            raise RuntimeError(f"StreamingCache lives on {cache.device}, the model on {self.device}")
+        if cache.arena.device != self.embed.device:
+            raise RuntimeError(f"StreamingCache lives on {cache.arena.device}, the model on {self.embed.device}")
         self.cache = cache
         self._graphs.clear()
         self._pf_graphs.clear()
