@@ -156,6 +156,16 @@ int svlm_vit_attn(const void* qkv, const int32_t* cu_seqlens, int n_seqs, void* 
  * ------------------------------------------------------------------------------------- */
 int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int M, int N, int K, int act,
                    const int32_t* out_rows, void* stream);
+/* The same persistent kernel with the epilogues the dense projections of the ViT blocks and of the chunk prefill need
+ * (HF nn.Linear call sites qwen2_5/language_forward.py:175-177, 255, 295-297 and qwen2_5/vision_forward.py:14, 36,
+ * 52), replacing cuBLAS + separate bias / activation / residual kernels:
+ *   epilogue 0: C = bf16(A W^T + bias)                     1: C = GELU(bf16(A W^T + bias))
+ *   epilogue 2: C = residual + bf16(A W^T + bias)          (residual bf16 [M][N], may alias C; the decoder's `hidden = residual + x`)
+ *   epilogue 3: SwiGLU: W holds gate and up rows interleaved in blocks of 64 ([gate 0:64 | up 0:64 | gate 64:128 | ...], N = 2 * width);
+ *               C [M][N/2] = bf16(silu(bf16(gate))) * bf16(up)  (`act_fn(gate_proj(x)) * up_proj(x)`), no bias
+ *   tile_n: 0 = chosen per shape from the measured UMMA costs, or 64 / 128 / 256 to force a tile width. */
+int svlm_gemm_bf16_ex(const void* A, const void* W, const void* bias, const void* residual, void* C, int M, int N, int K,
+                      int epilogue, const int32_t* out_rows, int tile_n, void* stream);
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
-           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16",
+           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
            "svlm_frames_to_patches", "svlm_frames_resize_bicubic",
            "svlm_kv_compact_rope_host"]
@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_vit_rope.argtypes = [vp, vp, vp, c_int, c_int, c_int, vp]
     L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
     L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
+    L.svlm_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, c_int, vp]
     L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_swiglu.argtypes = [vp, vp, c_int, c_int, c_int64, c_int64, vp]
@@ -217,6 +218,27 @@ def gemm_bf16(a, w, bias, out, act: int = 0, out_rows=None):
     assert w.shape[1] == k and a.is_contiguous() and w.is_contiguous() and out.is_contiguous()
     check(lib().svlm_gemm_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k, act, _ptr(out_rows), _stream()),
           "svlm_gemm_bf16")
+
+
+EPI_NONE, EPI_GELU, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2, 3
+
+
+def gemm_ex(a, w, out, bias=None, residual=None, epilogue: int = EPI_NONE, out_rows=None, tile_n: int = 0):
+    """out = epilogue(a @ w.T + bias) on the persistent tcgen05 GEMM (see include/svlm_b200.h, svlm_gemm_bf16_ex)."""
+    _req_cuda(a, w, out, bias, residual)
+    m, k = a.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and a.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    assert out.shape[1] == (n // 2 if epilogue == EPI_SWIGLU else n)
+    check(lib().svlm_gemm_bf16_ex(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), m, n, k, epilogue, _ptr(out_rows),
+                                  tile_n, _stream()), "svlm_gemm_bf16_ex")
+
+
+def interleave_gate_up(gate, up, block: int = 64):
+    """[gate rows ; up rows] -> rows interleaved in blocks of `block` (the layout the SwiGLU epilogue pairs inside one tile)."""
+    n, k = gate.shape
+    assert up.shape == gate.shape and n % block == 0
+    return torch.stack((gate.reshape(n // block, block, k), up.reshape(n // block, block, k)), dim=1).reshape(2 * n, k).contiguous()
 
 
 def gemv_bf16(w, x, y, mode: int = 0, norm_weight=None, eps: float = 1e-6, bias=None, residual=None):

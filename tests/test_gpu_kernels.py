@@ -684,3 +684,43 @@ def test_qkv_rope_append_without_queries(abi, tables):
     assert torch.equal(bits(got[0, 1, 1, :, start:start + t]), bits(want_rot[0]))
     assert torch.equal(bits(got[0, 2, 1, :, start:start + t]), bits(v.view(t, H, 128).transpose(0, 1)))
     assert got[0, :, 0].abs().sum() == 0 and got[0, :, 1, :, :start].abs().sum() == 0          # nothing else was touched
+
+
+# ------------------------------------------------------------------------------------------------ persistent GEMM epilogues
+@pytest.mark.parametrize("m,n,k,tile", [(300, 1280, 1280, 0), (1024, 3840, 1280, 256), (77, 3584, 1176, 64), (256, 512, 5120, 128),
+                                         (1024, 1280, 3456, 0), (640, 2560, 192, 256)])
+def test_gemm_ex_bias_and_residual(abi, m, n, k, tile):
+    """Persistent tcgen05 GEMM (several tiles per CTA, two TMEM accumulators) vs fp32 reference of the same op order: plain, bias,
+    residual add (`hidden = residual + bf16(linear)`), every tile width, ragged M / N / K tails."""
+    g = torch.Generator().manual_seed(m + n)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    bias = (torch.randn(n, generator=g) * 0.2).to(torch.bfloat16)
+    res = torch.randn(m, n, generator=g).to(torch.bfloat16)
+    lin = (a.float() @ w.float().t() + bias.float()).to(torch.bfloat16)
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_ex(a.to(DEV), w.to(DEV), out, bias=bias.to(DEV), tile_n=tile)
+    torch.testing.assert_close(out.cpu().float(), lin.float(), rtol=1.6e-2, atol=1e-2)
+    abi.gemm_ex(a.to(DEV), w.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV), epilogue=abi.EPI_RESIDUAL, tile_n=tile)
+    want = (lin.float() + res.float()).to(torch.bfloat16)
+    torch.testing.assert_close(out.cpu().float(), want.float(), rtol=1.6e-2, atol=1.6e-2)
+    # in place on the residual stream
+    x = res.to(DEV).clone()
+    abi.gemm_ex(a.to(DEV), w.to(DEV), x, bias=bias.to(DEV), residual=x, epilogue=abi.EPI_RESIDUAL, tile_n=tile)
+    assert torch.equal(bits(x.cpu()), bits(out.cpu()))
+
+
+@pytest.mark.parametrize("m,width,k", [(300, 1024, 512), (1024, 3456, 1280), (17, 18944, 3584)])
+def test_gemm_ex_swiglu(abi, m, width, k):
+    """SwiGLU epilogue on gate / up rows interleaved in blocks of 64: == silu(bf16(x Wg^T)) * bf16(x Wu^T) with the reference's roundings."""
+    g = torch.Generator().manual_seed(width)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16)
+    wg = (torch.randn(width, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    wu = (torch.randn(width, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    gate = (a.float() @ wg.float().t()).to(torch.bfloat16)
+    up = (a.float() @ wu.float().t()).to(torch.bfloat16)
+    want = (torch.nn.functional.silu(gate.float()).to(torch.bfloat16).float() * up.float()).to(torch.bfloat16)
+    w = abi.interleave_gate_up(wg, wu).to(DEV)
+    out = torch.empty(m, width, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_ex(a.to(DEV), w, out, epilogue=abi.EPI_SWIGLU)
+    torch.testing.assert_close(out.cpu().float(), want.float(), rtol=2e-2, atol=1e-2)
