@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Head-sharded tensor parallelism over NCCL (BASELINE configs[4]); launch with torchrun, one rank per GPU:
+"""Head-sharded tensor parallelism (BASELINE configs[4]): row-parallel projections reduced by our own one-shot all-reduce kernels over
+NVLink symmetric memory (svlm_tp_gemv_allreduce / svlm_tp_allreduce_rows), CUDA graphs on; NCCL only sets the group up.  Launch with
+torchrun, one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 benchmarks/tp_parity_and_bench.py parity
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 benchmarks/tp_parity_and_bench.py bench32b
@@ -18,7 +20,7 @@ from streaming_vlm_b200.config import QWEN25VL_32B, TINY
 from streaming_vlm_b200.engine import StreamingEngine
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
-use_graph = True        # the engine itself falls back to eager steps under TP unless SVLM_TP_GRAPH=1 (see StreamingEngine.__init__)
+use_graph = os.environ.get("SVLM_TP_EAGER", "0") != "1"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -53,8 +55,13 @@ if mode == "parity":
             mism += a != b
     assert tp.cache.compactions >= 6
     assert mism <= max(2, total // 20), (mism, total)
+    # every rank must hold the same stream: the all-reduce sums in rank order on every rank, so x is bit-identical everywhere
+    digest = [None] * world
+    dist.all_gather_object(digest, (tp.prev_ids.tolist(), tp.cache.seq_len))
+    assert all(d == digest[0] for d in digest), "ranks disagree on the generated stream"
     print(json.dumps({"mode": "parity", "rank": rank, "tp": world, "chunks": 12, "tokens": total, "argmax_mismatches_vs_unsharded": mism,
-                      "compactions": tp.cache.compactions, "kv_heads_local": local_geo.num_kv_heads}), flush=True)
+                      "compactions": tp.cache.compactions, "kv_heads_local": local_geo.num_kv_heads, "all_reduces": tp.tp.all_reduces,
+                      "cuda_graphs": use_graph}), flush=True)
 else:
     geo = QWEN25VL_32B
     w = synthetic.random_weights(geo, seed=0, device=dev)
@@ -82,7 +89,10 @@ else:
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
+        ar_per_token = 2 * geo.num_layers
         print(json.dumps({"mode": "bench32b", "geometry": geo.name, "tp": world, "frames_per_s": 2 * steps / float(t), "ms_per_chunk": 1e3 * float(t) / steps,
-                          "decode_tok_s": toks / float(t), "kv_len": eng.cache.seq_len, "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+                          "decode_tok_s": toks / float(t), "kv_len": eng.cache.seq_len, "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+                          "cuda_graphs": use_graph, "all_reduces_per_token": ar_per_token,
+                          "nvlink_bytes_pulled_per_token_per_rank": ar_per_token * eng.tp.nvlink_bytes_per_decode_allreduce()}), flush=True)
 dist.barrier()
 dist.destroy_process_group()

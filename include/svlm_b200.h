@@ -41,6 +41,7 @@ extern "C" {
 
 #define SVLM_MAX_RUNS 32   /* maximum number of gather runs per compaction launch */
 #define SVLM_MAX_STREAMS 8 /* streams whose decode steps share one launch (section 8) */
+#define SVLM_MAX_TP 8      /* ranks of one tensor-parallel group (one NVLink / NVSwitch node) */
 
 #define SVLM_PLANE_K_RAW 0
 #define SVLM_PLANE_K_ROT 1
@@ -283,6 +284,37 @@ int svlm_frames_to_patches(const void* frames_thwc_u8, int n_frames, int height,
 int svlm_frames_resize_bicubic(const void* in_thwc_u8, int n_frames, int height, int width, void* out_thwc_u8, int out_height,
                                int out_width, void* tmp_f32, const int32_t* x_start, const int32_t* x_count, const float* x_weights,
                                int kx, const int32_t* y_start, const int32_t* y_count, const float* y_weights, int ky, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (10) Head-sharded tensor parallelism over NVLink peer memory (BASELINE configs[4]; the reference has no such mode -- new
+ * functionality).  Rank r owns a slice of the q / kv heads and of the MLP width; the two row-parallel
+ * projections of a decoder layer (o_proj, down_proj) produce PARTIAL sums that have to be added over the ranks.  Instead of an
+ * NCCL all-reduce + a residual-add kernel per projection, the partial sums go to a buffer in SYMMETRIC memory (same allocation
+ * on every rank, every rank has every peer's copy mapped: torch.distributed._symmetric_memory or cuMem fabric handles) and the
+ * reduction is a one-shot exchange over NVLink loads inside our own kernels -- no NCCL call, CUDA-graph capturable:
+ *   svlm_tp_gemv_allreduce : decode step.  y = residual + bf16(sum_r W_r x_r): each CTA streams its rows of W (bf16 [N][K_local]),
+ *       writes fp32 partial sums into this rank's region; the CTA that finishes last announces the epoch to all peers (release
+ *       store into their flag arrays), waits for theirs, sums the W partial vectors in rank order, adds the residual, writes y.
+ *   svlm_tp_allreduce_rows : chunk prefill.  The partial products [rows][cols] bf16 were written into this rank's region by the
+ *       GEMM (svlm_tp_ctx_t offsets below); out = residual + bf16(sum_r part_r).
+ * Symmetric buffer layout (bytes, identical on every rank):  [0, 1024) flag words (uint32 per peer rank), then two regions of
+ * `region_bytes` for decode partials (fp32 [N]: which = 0 attention output, 1 MLP output) at SVLM_TP_DECODE_OFFSET, then two
+ * regions of `region_bytes` for row partials (bf16 [rows][cols]) behind them.  Two regions (`which`) are what makes reuse safe
+ * without a trailing barrier: a region is rewritten only after every peer has passed the NEXT all-reduce.
+ * `seq` / `done`: two zero-initialised uint32 in LOCAL device memory owned by the context. */
+typedef struct {
+    int32_t   world, rank;
+    void*     peer_base[SVLM_MAX_TP];   /* peer_base[r]: rank r's symmetric buffer as mapped in this process (peer_base[rank] = own) */
+    uint64_t  region_bytes;             /* size of each of the four partial regions */
+    uint32_t* seq;                      /* local device counter: all-reduces completed (the epoch) */
+    uint32_t* done;                     /* local device counter: finished CTAs of the running launch */
+} svlm_tp_ctx_t;
+#define SVLM_TP_DECODE_OFFSET 1024
+#define SVLM_TP_ROWS_OFFSET(ctx) (SVLM_TP_DECODE_OFFSET + 2 * (size_t)(ctx)->region_bytes)
+#define SVLM_TP_BUFFER_BYTES(region_bytes) (SVLM_TP_DECODE_OFFSET + 4 * (size_t)(region_bytes))
+int svlm_tp_gemv_allreduce(const svlm_tp_ctx_t* ctx, int which, const void* W, const void* x, const void* residual, void* y,
+                           int N, int K, void* stream);
+int svlm_tp_allreduce_rows(const svlm_tp_ctx_t* ctx, int which, const void* residual, void* out, int rows, int cols, void* stream);
 
 /* Scheduling aid of the decode loop (no reference counterpart: the reference leaves cache policy to the libraries it
  * calls): issues L2 prefetches for [ptr, ptr + bytes).  The session runner launches it on a side stream next to the

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
-           "svlm_frames_to_patches", "svlm_frames_resize_bicubic",
+           "svlm_frames_to_patches", "svlm_frames_resize_bicubic", "svlm_tp_gemv_allreduce", "svlm_tp_allreduce_rows",
            "svlm_kv_compact_rope_host"]
 
 MAX_RUNS = 32
@@ -41,6 +41,14 @@ class StreamSlot(Structure):
 
 
 MAX_STREAMS = 8
+MAX_TP = 8
+TP_DECODE_OFFSET = 1024
+
+
+class TpCtx(Structure):
+    """`svlm_tp_ctx_t` (include/svlm_b200.h section 10)."""
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("peer_base", c_void_p * MAX_TP), ("region_bytes", ctypes.c_uint64),
+                ("seq", c_void_p), ("done", c_void_p)]
 
 
 def needs_build() -> bool:
@@ -101,6 +109,8 @@ def lib() -> ctypes.CDLL:
     L.svlm_mark_seen.argtypes = [vp, c_int, vp, c_int64, c_int, vp]
     L.svlm_embed_tokens.argtypes = [vp, c_int, c_int64, vp, c_int64, vp, c_int, c_int, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
+    L.svlm_tp_gemv_allreduce.argtypes = [POINTER(TpCtx), c_int, vp, vp, vp, vp, c_int, c_int, vp]
+    L.svlm_tp_allreduce_rows.argtypes = [POINTER(TpCtx), c_int, vp, vp, c_int, c_int, vp]
     L.svlm_frames_resize_bicubic.argtypes = [vp, c_int, c_int, c_int, vp, c_int, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp]
     L.svlm_frames_to_patches.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), vp, c_int, vp]
     L.svlm_qkv_rope_append_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int,
@@ -296,6 +306,19 @@ def embed_tokens(ids, n: int, embed, video, n_video: int, out, status=None, vide
     assert ids.dtype == torch.int64 and embed.is_contiguous() and out.is_contiguous() and (video is None or video.is_contiguous())
     check(lib().svlm_embed_tokens(ids.data_ptr(), n, video_token_id, embed.data_ptr(), embed.shape[0], _ptr(video), n_video, embed.shape[1],
                                   out.data_ptr(), _ptr(status), _stream()), "svlm_embed_tokens")
+
+
+def tp_gemv_allreduce(ctx_ref, which: int, w, x, residual, y):
+    """y = residual + bf16(sum over ranks of W_r x_r): row-parallel GEMV fused with the one-shot all-reduce over NVLink peer memory."""
+    _req_cuda(w, x, residual, y)
+    check(lib().svlm_tp_gemv_allreduce(ctx_ref, which, w.data_ptr(), x.data_ptr(), residual.data_ptr(), y.data_ptr(), y.numel(), w.shape[1],
+                                       _stream()), "svlm_tp_gemv_allreduce")
+
+
+def tp_allreduce_rows(ctx_ref, which: int, residual, out, rows: int, cols: int):
+    """out = residual + bf16(sum over ranks of the bf16 partial products sitting in region `which` of the symmetric buffer)."""
+    _req_cuda(residual, out)
+    check(lib().svlm_tp_allreduce_rows(ctx_ref, which, residual.data_ptr(), out.data_ptr(), rows, cols, _stream()), "svlm_tp_allreduce_rows")
 
 
 def make_slots(caches, row_devs, pos_devs, kv_len_devs):

@@ -15,7 +15,55 @@
 namespace svlm {
 
 constexpr int GEMV_THREADS = 256;
-enum { GEMV_PLAIN = 0, GEMV_RESID = 1, GEMV_SWIGLU = 2, GEMV_ARGMAX = 3, GEMV_QKV = 4 };
+enum { GEMV_PLAIN = 0, GEMV_RESID = 1, GEMV_SWIGLU = 2, GEMV_ARGMAX = 3, GEMV_QKV = 4, GEMV_TP = 5 };
+
+// Tensor-parallel all-reduce state as the kernels see it (built from svlm_tp_ctx_t): every rank's partial-sum buffer and flag
+// array live in symmetric memory that all ranks of the node have mapped (NVLink peer access).
+struct TpDev {
+    int world, rank;
+    const void* peer_part[SVLM_MAX_TP];     // rank r's partial buffer for THIS all-reduce, as mapped here
+    uint32_t* peer_flags[SVLM_MAX_TP];      // rank r's flag array [SVLM_MAX_TP]; flags[q] = last epoch rank q announced to r
+    uint32_t* seq;                          // local: all-reduces completed so far (the epoch counter)
+    uint32_t* done;                         // local: CTAs of the current launch that have finished their part (0 between launches)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-rank rendezvous of one all-reduce, executed by ONE CTA per rank once this rank's partial sums are complete and visible:
+// announce epoch = *seq + 1 to every peer (release store into the peer's flag array over NVLink), then wait until every peer has
+// announced the same epoch to us.  A rank that never shows up turns into a trap after ~2 s instead of a hung GPU.
+__device__ __forceinline__ uint32_t tp_rendezvous(const TpDev& tp) {
+    const uint32_t epoch = *tp.seq + 1u;
+    __threadfence_system();
+    if ((int)threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+        st_release_sys(tp.peer_flags[threadIdx.x] + tp.rank, epoch);
+        const uint32_t* mine = tp.peer_flags[tp.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > 4000000000ll) {
+                printf("svlm: tensor-parallel all-reduce timed out (rank %d waiting for rank %d, epoch %u)\n", tp.rank, (int)threadIdx.x, epoch);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    return epoch;
+}
 
 struct GemvParams {
     const uint16_t* W;
@@ -50,6 +98,10 @@ struct GemvParams {
     int do_sample;              // 1: Gumbel-max sample of softmax(score); 0: argmax of the processed score
     const uint32_t* rng;        // device [4]: Philox key (seed lo, seed hi), counter word 1 = step (advanced by decode_finalize_kernel), reserved
     float* scores_out;          // [N] processed scores (HF `output_scores`), or NULL
+    // GEMV_TP: row-parallel projection of a tensor-parallel rank -- fp32 partial sums into symmetric memory, one-shot all-reduce
+    // over NVLink peer loads and the residual add, all in this kernel
+    float* tp_part;             // this rank's partial buffer [N] fp32 (== tp.peer_part[tp.rank])
+    TpDev tp;
 };
 
 // Philox4x32-10 (Salmon et al.), counter (c0, c1, 0, 0), key = seed: one uniform per (vocabulary row, step)
@@ -270,6 +322,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
                 } else if (p.scores_out) {
                     p.scores_out[n] = -INFINITY;
                 }
+            } else if (MODE == GEMV_TP) {
+                p.tp_part[n] = v;                                                  // fp32 partial sum of this rank's K slice
             } else if (MODE == GEMV_SWIGLU) {
                 const float gt = round_bf16(v), up = round_bf16(v2);
                 const float sl = round_bf16(gt / (1.0f + __expf(-gt)));
@@ -291,6 +345,90 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
             if (bb) atomicMax(p.key, bb);
         }
     }
+    if (MODE == GEMV_TP) {
+        // The CTA that finishes last owns the all-reduce: every other CTA's partial sums are visible to it (fence + counter),
+        // it meets the peer ranks, sums the W partial vectors in rank order (the same order on every rank: bit-identical
+        // results everywhere), rounds to bf16 like the unsharded Linear does, adds the residual and writes y.
+        __shared__ int is_last;
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            is_last = atomicAdd(p.tp.done, 1u) == gridDim.x - 1;
+            __threadfence();
+        }
+        __syncthreads();
+        if (!is_last) return;
+        const uint32_t epoch = tp_rendezvous(p.tp);
+        for (int n = t * 4; n < p.N; n += GEMV_THREADS * 4) {
+            float4 part[SVLM_MAX_TP];
+#pragma unroll
+            for (int r = 0; r < SVLM_MAX_TP; ++r)
+                if (r < p.tp.world) part[r] = ld_relaxed_sys_f4(reinterpret_cast<const float*>(p.tp.peer_part[r]) + n);
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < SVLM_MAX_TP; ++r)
+                if (r < p.tp.world) { sum.x += part[r].x; sum.y += part[r].y; sum.z += part[r].z; sum.w += part[r].w; }
+            const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + n);
+            uint2 o;
+            o.x = pack_bf16(round_bf16(sum.x) + bf16_lo(rv.x), round_bf16(sum.y) + bf16_hi(rv.x));
+            o.y = pack_bf16(round_bf16(sum.z) + bf16_lo(rv.y), round_bf16(sum.w) + bf16_hi(rv.y));
+            *reinterpret_cast<uint2*>(p.y + n) = o;
+        }
+        if (t == 0) { *p.tp.seq = epoch; *p.tp.done = 0u; }
+    }
+}
+
+// Stand-alone all-reduce + residual add over rows of bf16 partial products (the chunk prefill's row-parallel projections, whose
+// partial products cuBLAS wrote into the symmetric buffer): out[t][n] = residual[t][n] + bf16(sum_r part_r[t][n]).  Block 0
+// performs the rendezvous' announcement; every CTA waits for the peers' flags, then reduces its slice over NVLink peer loads.
+__global__ void __launch_bounds__(256) tp_allreduce_rows_kernel(const TpDev tp, const uint16_t* __restrict__ residual, uint16_t* __restrict__ out,
+                                                                 int64_t n_elems) {
+    __shared__ int is_last;
+    const uint32_t epoch = *tp.seq + 1u;
+    if (blockIdx.x == 0 && (int)threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+        __threadfence_system();
+        st_release_sys(tp.peer_flags[threadIdx.x] + tp.rank, epoch);
+    }
+    if ((int)threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+        const uint32_t* mine = tp.peer_flags[tp.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > 4000000000ll) {
+                printf("svlm: tensor-parallel all-reduce (rows) timed out (rank %d waiting for rank %d, epoch %u)\n", tp.rank, (int)threadIdx.x, epoch);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8; i < n_elems; i += (int64_t)gridDim.x * 256 * 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 part[SVLM_MAX_TP];
+#pragma unroll
+        for (int r = 0; r < SVLM_MAX_TP; ++r)
+            if (r < tp.world) part[r] = ld_relaxed_sys_u4(reinterpret_cast<const uint16_t*>(tp.peer_part[r]) + i);
+#pragma unroll
+        for (int r = 0; r < SVLM_MAX_TP; ++r) {
+            if (r < tp.world) {
+                const uint32_t* q = &part[r].x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc[2 * k] += bf16_lo(q[k]); acc[2 * k + 1] += bf16_hi(q[k]); }
+            }
+        }
+        const uint4 rv = *reinterpret_cast<const uint4*>(residual + i);
+        const uint32_t* pr = &rv.x;
+        uint4 o;
+        uint32_t* po = &o.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) po[k] = pack_bf16(round_bf16(acc[2 * k]) + bf16_lo(pr[k]), round_bf16(acc[2 * k + 1]) + bf16_hi(pr[k]));
+        *reinterpret_cast<uint4*>(out + i) = o;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(tp.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) { *tp.seq = epoch; *tp.done = 0u; }
 }
 
 // token id + device-side counters of the decode loop (kv length before / after the next step, next text position)
@@ -375,6 +513,7 @@ static int dispatch_shape(const GemvParams& p, cudaStream_t st) {
         if (rc != -100) return rc;
     }
 #endif
+    if (MODE == GEMV_TP) return p.K >= 8192 ? launch_gemv<MODE, 2, 4, 2, STAGE>(p, st) : launch_gemv<MODE, 4, 4, 4, STAGE>(p, st);
     if (MODE == GEMV_SWIGLU) return launch_gemv<MODE, 2, 1, 2, STAGE>(p, st);
     if (MODE == GEMV_ARGMAX) return launch_gemv<MODE, 4, 1, 2, STAGE>(p, st);
     if (p.K >= 8192) return launch_gemv<MODE, 2, 4, 2, STAGE>(p, st);     // swept (benchmarks/gemv_tune.py): 24.2 us vs 27.0 for <4,8,2>
@@ -486,4 +625,55 @@ extern "C" int svlm_prefetch_l2(const void* ptr, size_t bytes, void* stream) {
     const unsigned grid = (unsigned)((lines + 256 * 16 - 1) / (256 * 16) < 296 ? (lines + 256 * 16 - 1) / (256 * 16) : 296);
     prefetch_l2_kernel<<<grid ? grid : 1, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)ptr, bytes);
     return launch_status("prefetch_l2_kernel");
+}
+
+
+// ------------------------------------------------------------------------------------------------ tensor parallelism
+static int make_tp_dev(const svlm_tp_ctx_t* ctx, int which, size_t region_offset, size_t bytes_needed, TpDev* out) {
+    SVLM_REQUIRE(ctx != nullptr, "tensor-parallel context is NULL");
+    SVLM_REQUIRE(ctx->world >= 2 && ctx->world <= SVLM_MAX_TP && ctx->rank >= 0 && ctx->rank < ctx->world, "bad world %d / rank %d", ctx->world,
+                 ctx->rank);
+    SVLM_REQUIRE(which == 0 || which == 1, "which must be 0 (attention output) or 1 (MLP output)");
+    SVLM_REQUIRE(ctx->seq && ctx->done, "NULL counter in the tensor-parallel context");
+    SVLM_REQUIRE(bytes_needed <= ctx->region_bytes, "partial products need %zu bytes, a region of the symmetric buffer has %zu", bytes_needed,
+                 (size_t)ctx->region_bytes);
+    out->world = ctx->world;
+    out->rank = ctx->rank;
+    for (int r = 0; r < ctx->world; ++r) {
+        SVLM_REQUIRE(ctx->peer_base[r] != nullptr, "peer %d is not mapped", r);
+        out->peer_flags[r] = reinterpret_cast<uint32_t*>(ctx->peer_base[r]);
+        out->peer_part[r] = reinterpret_cast<const char*>(ctx->peer_base[r]) + region_offset + (size_t)which * ctx->region_bytes;
+    }
+    out->seq = ctx->seq;
+    out->done = ctx->done;
+    return SVLM_OK;
+}
+
+extern "C" int svlm_tp_gemv_allreduce(const svlm_tp_ctx_t* ctx, int which, const void* W, const void* x, const void* residual, void* y, int N,
+                                      int K, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    if ((rc = gemv_common_checks(W, x, y, N, K))) return rc;
+    SVLM_REQUIRE(residual != nullptr && N % 4 == 0, "residual is NULL or N %d is not a multiple of 4", N);
+    GemvParams p{(const uint16_t*)W, (const uint16_t*)x, nullptr, 0.f, nullptr, (const uint16_t*)residual, (uint16_t*)y, N, K, nullptr, nullptr};
+    if ((rc = make_tp_dev(ctx, which, SVLM_TP_DECODE_OFFSET, (size_t)N * sizeof(float), &p.tp))) return rc;
+    p.tp_part = const_cast<float*>(reinterpret_cast<const float*>(p.tp.peer_part[ctx->rank]));
+    return dispatch_shape<GEMV_TP, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int svlm_tp_allreduce_rows(const svlm_tp_ctx_t* ctx, int which, const void* residual, void* out, int rows, int cols, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(residual && out && rows > 0 && cols > 0 && cols % 8 == 0, "bad rows / cols / NULL tensor");
+    SVLM_REQUIRE((((uintptr_t)residual | (uintptr_t)out) & 15) == 0, "residual / out must be 16-byte aligned");
+    TpDev tp;
+    const size_t bytes = (size_t)rows * cols * 2;
+    if ((rc = make_tp_dev(ctx, which, SVLM_TP_ROWS_OFFSET(ctx), bytes, &tp))) return rc;
+    const int64_t n = (int64_t)rows * cols;
+    int grid = (int)((n / 8 + 255) / 256);
+    grid = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
+    // plain launch (no programmatic dependent launch): the producer of the partial products is a library GEMM that may signal its
+    // dependents early; this kernel must not start before that grid has completed
+    tp_allreduce_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, (const uint16_t*)residual, (uint16_t*)out, n);
+    return launch_status("tp_allreduce_rows_kernel");
 }

@@ -144,12 +144,14 @@ class StreamingEngine:
         _abi.lib()
         # head-sharded tensor parallelism (parallel.shard_llm_weights): `geo` and `weights` are this rank's shard, `tp_group` the
         # NCCL group whose all-reduce sums the o_proj / down_proj partial products
+        # NCCL group whose ranks hold the other shards.  The two row-parallel projections of a layer are reduced by our own kernels over
+        # symmetric memory (parallel.TpContext): no NCCL call on the data path, so the steps stay CUDA-graph capturable (replaying
+        # graphs that contained NCCL all-reduces hung on this pool in round 1, which had forced this mode to run eagerly).
         self.tp_group = tp_group
+        self.tp = None
         if tp_group is not None:
-            # Replaying CUDA graphs that contain the NCCL all-reduces hung on this pool (both ranks stuck in the first replay, with
-            # or without the side-stream prefetch, with or without NCCL_GRAPH_MIXING_SUPPORT=0); the tensor-parallel mode
-            # therefore runs its steps eagerly unless SVLM_TP_GRAPH=1 asks for the experiment.
-            use_graph = use_graph and os.environ.get("SVLM_TP_GRAPH", "0") == "1"
+            from .parallel import TpContext
+            self.tp = TpContext(tp_group, geo.hidden, max_rows=1024, device=device)
         self.geo, self.device = geo, torch.device(device)
         self.window_size, self.text_round = window_size, text_round
         self.text_sink, self.text_sliding_window = text_sink, text_sliding_window
@@ -351,12 +353,17 @@ class StreamingEngine:
             e.record()
             marks.append((name, e, time.perf_counter()))
 
-    def _reduce(self, t):
-        """Sum of the row-parallel partial products over the tensor-parallel group (identity without one)."""
-        if self.tp_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(t, group=self.tp_group)
-        return t
+    def _row_parallel(self, which, a, w, x):
+        """Tensor-parallel rank: x + sum over ranks of (a @ w.T).  The GEMM writes this rank's partial products straight into the
+        symmetric buffer; `svlm_tp_allreduce_rows` reduces them over NVLink peer loads and adds the residual."""
+        t = a.shape[0]
+        part = self.tp.rows_view(which, t, w.shape[0])
+        torch.mm(a, w.t(), out=part)
+        out = torch.empty_like(x)
+        _abi.tp_allreduce_rows(self.tp.ref, which, x, out, t, w.shape[0])
+        self.tp.all_reduces += 1
+        self.launches += 1
+        return out
 
     def _rmsnorm(self, x, w, eps=1e-6):
         out = torch.empty_like(x)
@@ -465,9 +472,14 @@ class StreamingEngine:
         if taps is not None:
             taps.setdefault("attn_out", []).append(o.view(t, -1))
             taps.setdefault("q_rot", []).append(q_rot)
-        x, h = self._add_norm(x, self._reduce(F.linear(o.view(t, -1), L["wo"])), L["ln2"], g.rms_eps)
+        if self.tp is None:
+            x, h = self._add_norm(x, F.linear(o.view(t, -1), L["wo"]), L["ln2"], g.rms_eps)
+            gu = F.linear(h, L["wgu"])
+            return x, F.linear(self._swiglu(gu, g.mlp), L["wd"])
+        x = self._row_parallel(0, o.view(t, -1), L["wo"], x)
+        _, h = self._add_norm(x, None, L["ln2"], g.rms_eps)
         gu = F.linear(h, L["wgu"])
-        return x, self._reduce(F.linear(self._swiglu(gu, g.mlp), L["wd"]))
+        return self._row_parallel(1, self._swiglu(gu, g.mlp), L["wd"], x), None
 
     def _logits(self, x_last, pending_last=None):
         _, h = self._add_norm(x_last, pending_last, self.norm, self.geo.rms_eps)
@@ -561,11 +573,11 @@ class StreamingEngine:
         for li in range(g.num_layers):
             x, pending = self._layer(x, pending, li, t_pad, start, self.cache.capacity if dev_start else start + t_pad, splits, taps, dev_start)
         if dev_start:           # padded prefill: the last REAL row is named by a device scalar
-            x_last, p_last = x.index_select(0, self._pf_last), pending.index_select(0, self._pf_last)
+            x_last, p_last = x.index_select(0, self._pf_last), None if pending is None else pending.index_select(0, self._pf_last)
         else:
-            x_last, p_last = x[t - 1:t], pending[t - 1:t]
+            x_last, p_last = x[t - 1:t], None if pending is None else pending[t - 1:t]
         if taps is not None:
-            taps["logits"] = self._logits(x_last.contiguous(), p_last.contiguous())[0]
+            taps["logits"] = self._logits(x_last.contiguous(), None if p_last is None else p_last.contiguous())[0]
         self._select_token(x_last, p_last, gen)
 
     # ------------------------------------------------------------------ decode (one token per CUDA-graph replay)
@@ -591,17 +603,15 @@ class StreamingEngine:
                              self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev)
             if self._prefetch:
                 main.wait_stream(self._side)
-            if self.tp_group is None:
+            if self.tp is None:
                 _abi.gemv_bf16(L["wo"], o.view(-1), x, 1, residual=x)
                 _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
                 _abi.gemv_bf16(L["wd"], act, x, 1, residual=x)
-            else:       # row-parallel projections: partial product -> all-reduce -> residual add
-                part = self._dec_part
-                _abi.gemv_bf16(L["wo"], o.view(-1), part, 0)
-                x.add_(self._reduce(part))
+            else:       # row-parallel projections: GEMV + one-shot all-reduce over NVLink + residual add, one kernel each
+                _abi.tp_gemv_allreduce(self.tp.ref, 0, L["wo"], o.view(-1), x, x)
                 _abi.gemv_bf16(L["wgu"], x, act, 2, L["ln2"], g.rms_eps)
-                _abi.gemv_bf16(L["wd"], act, part, 0)
-                x.add_(self._reduce(part))
+                _abi.tp_gemv_allreduce(self.tp.ref, 1, L["wd"], act, x, x)
+                self.tp.all_reduces += 2
         self.launches += g.num_layers * (5 + (1 if self._splits_now > 1 else 0) + ((2 if self._prefetch_gu_bytes else 1) if self._prefetch else 0))
         _abi.lm_head_sample(self.lm_head, x, self.norm, g.rms_eps, self.suppress_u8, self._argmax_key, self.tok_dev,
                             self.kv_len_dev, self.kv_after_dev, c.next_pos, seen=self.seen, repetition_penalty=gen.repetition_penalty,

@@ -62,3 +62,56 @@ def shard_llm_weights(weights: dict, geo, rank: int, world: int):
         out[name] = t.contiguous()
     local = replace(geo, num_heads=geo.num_heads // world, num_kv_heads=geo.num_kv_heads // world, mlp=geo.mlp // world)
     return out, local
+
+
+class TpContext:
+    """Symmetric-memory state of one tensor-parallel group on this rank (`svlm_tp_ctx_t`): one buffer of the same size on every
+    rank, every peer's copy mapped into this process over NVLink (`torch.distributed._symmetric_memory`: CUDA VMM + fabric / fd
+    handles; plumbing only -- the exchange itself is `svlm_tp_gemv_allreduce` / `svlm_tp_allreduce_rows`, no NCCL call on the
+    data path).  Collective: every rank of `group` must construct it at the same time."""
+
+    def __init__(self, group, hidden: int, max_rows: int = 1024, device=None):
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _abi
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not 2 <= self.world <= _abi.MAX_TP:
+            raise ValueError(f"tensor-parallel degree must be 2..{_abi.MAX_TP}, got {self.world}")
+        dev = torch.device(device if device is not None else torch.cuda.current_device())
+        self.hidden, self.max_rows = hidden, max_rows
+        self.region = -(-max(hidden * 4, max_rows * hidden * 2) // 1024) * 1024
+        nbytes = _abi.TP_DECODE_OFFSET + 4 * self.region
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.buf.zero_()
+        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)        # seq, done
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                                                  # every rank's flags are zero before anyone signals
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected peer table")
+        self.c = _abi.TpCtx()
+        self.c.world, self.c.rank = self.world, self.rank
+        for r, p_ in enumerate(ptrs):
+            self.c.peer_base[r] = p_
+        self.c.region_bytes = self.region
+        self.c.seq = self.counters[0:1].data_ptr()
+        self.c.done = self.counters[1:2].data_ptr()
+        self.ref = ctypes.byref(self.c)
+        self.all_reduces = 0
+
+    def rows_view(self, which: int, rows: int, cols: int):
+        """bf16 [rows, cols] view of region `which` of this rank's row-partial area: the GEMM writes its partial products here."""
+        from . import _abi
+        if rows * cols * 2 > self.region:
+            raise RuntimeError(f"{rows} x {cols} partial products do not fit a {self.region}-byte region (max_rows = {self.max_rows})")
+        off = _abi.TP_DECODE_OFFSET + (2 + which) * self.region
+        return self.buf[off:off + rows * cols * 2].view(torch.bfloat16).view(rows, cols)
+
+    def nvlink_bytes_per_decode_allreduce(self):
+        """Bytes this rank pulls over NVLink in one decode all-reduce: (world - 1) peers x hidden fp32 partial sums."""
+        return (self.world - 1) * self.hidden * 4
