@@ -694,6 +694,84 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_tp(args):
+    """BASELINE.json configs[4]: ONE stream of the 32B (or 7B) architecture, its language model head-sharded over the `--tp` ranks
+    of this torchrun job.  The row-parallel projections are reduced by our own kernels over NVLink symmetric memory (no NCCL on the
+    data path), every step is a CUDA-graph replay.  `value` = frames/s of the one stream (strong scaling: the work is fixed)."""
+    import torch.distributed as dist
+    from streaming_vlm_b200 import _abi, parallel, synthetic
+    from streaming_vlm_b200.config import PRESETS
+    from streaming_vlm_b200.engine import StreamingEngine
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.tp:
+        raise RuntimeError(f"--tp {args.tp} needs a torchrun job of {args.tp} ranks (got WORLD_SIZE = {world})")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    geo = PRESETS[args.geometry]
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.ones(1, device=dev))
+    _abi.build()
+    w = synthetic.random_weights(geo, seed=0, device=dev)
+    if world > 1:
+        w, local_geo = parallel.shard_llm_weights(w, geo, rank, world)
+    else:
+        local_geo = geo
+    torch.cuda.empty_cache()
+    eng = StreamingEngine(w, local_geo, capacity=8192, device=dev, suppress=synthetic.suppress_mask(geo.vocab),
+                          tp_group=dist.group.WORLD if world > 1 else None)
+    del w
+    torch.cuda.empty_cache()
+    eng.load_state(synthetic.fast_forward(STEADY_ROUNDS, new_tokens=NEW_TOKENS, seed=0), seed=0)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    base = eng.i
+    frames = [synthetic.frames(base + k).permute(0, 2, 3, 1).contiguous().pin_memory() for k in range(steps + warmup)]
+    prompts = [synthetic.round_prompt(base + k) for k in range(steps + warmup)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(warmup):
+        eng.step(prompts[k], None, None, sync_timing=False, frames=frames[k].to(dev))
+    barrier()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        toks = 0
+        for k in range(warmup, warmup + steps):
+            r = eng.step(prompts[k], None, None, sync_timing=False, frames=frames[k].to(dev, non_blocking=True))
+            toks += min(len(r["new_tokens"]), NEW_TOKENS)
+        e1.record()
+        barrier()
+    t = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    if rank == 0:
+        ar = 2 * geo.num_layers
+        line = {"metric": METRIC, "value": steps * FRAMES_PER_CHUNK / t, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"configs[4]: {geo.name} random-init, ONE stream, language model head-sharded over {world} GPU(s) "
+                                       "(q/k/v/gate/up column-parallel, o_proj/down_proj row-parallel + one-shot all-reduce over NVLink symmetric "
+                                       "memory inside svlm_tp_gemv_allreduce / svlm_tp_allreduce_rows), steady state S~5.8k, 20 tokens per chunk, greedy",
+                           "tp": world, "geometry": args.geometry, "cuda_graphs": True,
+                           "cache_flush": "inputs larger than L2 (the weight shard of every rank is swept every token)"},
+                "decode_tok_s": toks / t, "gpu_launches": eng.launches - l0, "clocks": clk.summary(), "kv_len": eng.cache.seq_len,
+                "e2e": {"value": steps * FRAMES_PER_CHUNK / t, "unit": UNIT, "h2d_bytes_per_step": frames[0].numel() + len(eng.prev_ids) * 8,
+                        "d2h_bytes_per_step": NEW_TOKENS * 8, "note": "the timed region itself copies the uint8 frames from pinned host memory and reads the tokens back"},
+                "all_reduces_per_token": ar if world > 1 else 0,
+                "nvlink_bytes_pulled_per_token_per_rank": ar * eng.tp.nvlink_bytes_per_decode_allreduce() if world > 1 else 0,
+                "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "cpu_baseline": None, "roofline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -705,12 +783,17 @@ def main():
     ap.add_argument("--generation", default="reference", choices=["reference", "greedy"],
                     help="token selection of the timed drop-in legs: the reference's sampling config or greedy")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[2] 4k-64k kernel sweep")
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel degree of ONE stream (configs[4]); the torchrun job must have that many ranks; "
+                                                      "1 = the same stream unsharded on one GPU")
+    ap.add_argument("--geometry", default="32b", choices=["7b", "32b"], help="model geometry of the --tp mode")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around timed region 1 (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)      # timing rule: at least 3 untimed warm-up steps (CUDA-graph capture happens there)
     if args.impl == "reference":
         run_reference(args)
+    elif args.tp:
+        run_tp(args)
     else:
         run_gpu(args)
 
