@@ -423,8 +423,9 @@ class DropInSession:
         self.args.video_grid_thw = torch.tensor([list(g) for g in state["grids"]], dtype=torch.long, device=dev)
         self.timing = []
 
-    def step(self, prompt_ids, frames_thwc):
+    def step(self, prompt_ids, frames_thwc, max_new_tokens=None):
         from streaming_vlm_b200.inference.inference import process_past_kv
+        max_new_tokens = NEW_TOKENS if max_new_tokens is None else int(max_new_tokens)
         torch.ops.svlm  # noqa: B018  (custom ops registered by convert_qwen2_5_to_streaming)
         i = self.i
         t0 = time.perf_counter()
@@ -446,7 +447,7 @@ class DropInSession:
         n_in = ids.shape[1]
         t0 = time.perf_counter()
         out = self.model.generate(input_ids=ids, pixel_values_videos=px, video_grid_thw=grid, past_key_values=self.past,
-                                  max_new_tokens=NEW_TOKENS, use_cache=True, return_dict_in_generate=True, streaming_args=self.args,
+                                  max_new_tokens=max_new_tokens, use_cache=True, return_dict_in_generate=True, streaming_args=self.args,
                                   pad_token_id=151645, suppress_tokens=self.sup, **self.gen_kwargs)
         t_gen = time.perf_counter() - t0
         seq = out.sequences
