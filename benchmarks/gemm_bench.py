@@ -63,7 +63,7 @@ def main():
         t = timed(lambda: [F.linear(a, ws[i % copies], bias) for i in range(reps)]) / reps
         rec["cublas_us"] = t * 1e6
         rec["cublas_tflops"] = rec["gflop"] / t / 1e3
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 64, 128, 256, 1064, 1128, 1256):          # 1000 + BN = CTA-pair kernel (256 x BN tiles, cta_group::2)
             try:
                 _abi.gemm_ex(a, ws[0], out, bias=bias, tile_n=bn)
                 torch.cuda.synchronize()

@@ -688,7 +688,10 @@ def test_qkv_rope_append_without_queries(abi, tables):
 
 # ------------------------------------------------------------------------------------------------ persistent GEMM epilogues
 @pytest.mark.parametrize("m,n,k,tile", [(300, 1280, 1280, 0), (1024, 3840, 1280, 256), (77, 3584, 1176, 64), (256, 512, 5120, 128),
-                                         (1024, 1280, 3456, 0), (640, 2560, 192, 256)])
+                                         (1024, 1280, 3456, 0), (640, 2560, 192, 256),
+                                         # 1000 + BN: the CTA-pair kernel (cta_group::2, 256 x BN tiles), incl. ragged M / N tails
+                                         (1024, 3840, 1280, 1256), (256, 5120, 5120, 1128), (300, 1288, 1280, 1064), (1000, 2600, 704, 1256),
+                                         (2048, 6912, 1280, 1128)])
 def test_gemm_ex_bias_and_residual(abi, m, n, k, tile):
     """Persistent tcgen05 GEMM (several tiles per CTA, two TMEM accumulators) vs fp32 reference of the same op order: plain, bias,
     residual add (`hidden = residual + bf16(linear)`), every tile width, ragged M / N / K tails."""
