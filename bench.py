@@ -471,6 +471,7 @@ def config3_sweep(pk, dev, sizes=(4096, 8192, 16384, 32768, 65536)):
     Split counts are the engine's own heuristics.  (benchmarks/microbench.py adds the reference's library calls on the same GPU.)"""
     from streaming_vlm_b200 import _abi
     from streaming_vlm_b200.config import QWEN25VL_7B as G
+    from streaming_vlm_b200.engine import decode_split_count
     from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
     L, H, HQ, D = G.num_layers, G.num_kv_heads, G.num_heads, G.head_dim
     scale = 1.0 / math.sqrt(D)
@@ -512,8 +513,7 @@ def config3_sweep(pk, dev, sizes=(4096, 8192, 16384, 32768, 65536)):
             q1 = torch.randn(1, HQ, D, device=dev).to(torch.bfloat16)
             o1 = torch.empty_like(q1)
             kv_dev = torch.tensor([keep], dtype=torch.int32, device=dev)
-            n_tiles = (keep + 128) // 128
-            splits = max(1, min(148 // H, -(-n_tiles // 2)))                      # StreamingEngine.decode_step
+            splits = decode_split_count(keep, H)                                  # StreamingEngine.decode_step
             ws = torch.zeros(max(_abi.attn_workspace_bytes(1, HQ, D, splits), _abi.attn_workspace_bytes(512, HQ, D, 4)) // 4 + 16,
                              dtype=torch.float32, device=dev)
             t = timed(lambda: [_abi.attn_causal(c.view, 1, li, q1, o1, 1, HQ, cap, scale, splits, ws, kv_len_dev=kv_dev) for li in range(L)]) / L

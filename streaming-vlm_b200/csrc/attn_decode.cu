@@ -36,10 +36,11 @@ struct DecParams {
     const int32_t* kv_len_dev[SVLM_MAX_STREAMS];      // per stream (blockIdx.z)
     int rows_total;                                   // n_streams * Hq: row count of out / the partials
     int num_splits;
+    int cluster;          // CTAs per cluster along the split axis: their partial (m, l, O) are merged through distributed shared memory
     int kv_head_base;
-    uint16_t* out;        // bf16 [streams][Hq][D]           (num_splits == 1)
-    float* part_o;        // fp32 [splits][streams * Hq][D]
-    float2* part_ml;      // (m, l) [splits][streams * Hq]
+    uint16_t* out;        // bf16 [streams][Hq][D]           (num_splits == cluster: nothing left to merge)
+    float* part_o;        // fp32 [splits / cluster][streams * Hq][D]
+    float2* part_ml;      // (m, l) [splits / cluster][streams * Hq]
     float scale_log2;
     unsigned long long* trace;   // SVLM_TRACE builds only: [cta][tile][8] clock64 stamps
 };
@@ -68,6 +69,11 @@ __device__ __forceinline__ int ordered_i32(float f) {            // monotonic fl
 }
 __device__ __forceinline__ float unordered_f32(int i) { return __int_as_float(i >= 0 ? i : (i ^ 0x7fffffff)); }
 
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -310,24 +316,76 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
             for (int h = 0; h < 8; ++h) orow[h] = 0u;
         }
         const int d = row;                         // O^T lane = head-dim index
-        if (d < p.D) {
+        if (p.cluster == 1) {
+            if (d < p.D) {
 #pragma unroll
-            for (int h = 0; h < G; ++h) {
-                const int hq = strm * p.Hq + head * G + h;       // row of out / the partials
-                if (p.num_splits == 1) {
-                    const float inv = l_tot[h] > 0.f ? 1.0f / l_tot[h] : 0.f;
-                    p.out[(int64_t)hq * p.D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(orow[h]) * inv));
-                } else {
-                    p.part_o[((int64_t)split * p.rows_total + hq) * p.D + d] = __uint_as_float(orow[h]);
+                for (int h = 0; h < G; ++h) {
+                    const int hq = strm * p.Hq + head * G + h;       // row of out / the partials
+                    if (p.num_splits == 1) {
+                        const float inv = l_tot[h] > 0.f ? 1.0f / l_tot[h] : 0.f;
+                        p.out[(int64_t)hq * p.D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(orow[h]) * inv));
+                    } else {
+                        p.part_o[((int64_t)split * p.rows_total + hq) * p.D + d] = __uint_as_float(orow[h]);
+                    }
+                }
+            }
+            if (p.num_splits > 1) {
+#pragma unroll
+                for (int h = 0; h < G; ++h)
+                    if (row == h) p.part_ml[(int64_t)split * p.rows_total + strm * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
+            }
+        } else {
+            // publish this split's (m, l, O^T) in shared memory for the cluster merge below; the P^T operand buffers are free
+            // (the last PV UMMA has completed) and hold G x 128 floats
+            float* xo = reinterpret_cast<float*>(sP);
+#pragma unroll
+            for (int h = 0; h < G; ++h) xo[h * 128 + d] = __uint_as_float(orow[h]);
+#pragma unroll
+            for (int h = 0; h < G; ++h)
+                if (row == h) { sh->wmax[0][0][h] = m_run[h]; sh->wmax[1][0][h] = l_tot[h]; }
+        }
+    }
+
+    if (p.cluster > 1) {
+        // ---- split merge inside the cluster: rank 0 reads every peer's (m, l, O^T) over distributed shared memory, so the partial
+        // sums of `cluster` splits never travel through HBM / L2 and (when cluster == num_splits) no merge kernel is launched
+        cluster_sync_all();
+        if (cluster_ctarank() == 0 && warp >= 2) {
+            const int d = (warp & 3) * 32 + lane;
+            const uint32_t xo_local = smem_u32(sP), m_local = smem_u32(&sh->wmax[0][0][0]), l_local = smem_u32(&sh->wmax[1][0][0]);
+            float M[G], L[G], O[G];
+#pragma unroll
+            for (int h = 0; h < G; ++h) { M[h] = -INFINITY; L[h] = 0.f; O[h] = 0.f; }
+            for (int r = 0; r < p.cluster; ++r) {
+                const uint32_t xo_r = mapa_shared(xo_local, r), m_r = mapa_shared(m_local, r), l_r = mapa_shared(l_local, r);
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const float m = ld_shared_cluster_f32(m_r + h * 4), l = ld_shared_cluster_f32(l_r + h * 4);
+                    const float o = ld_shared_cluster_f32(xo_r + (h * 128 + d) * 4);
+                    const float m_new = fmaxf(M[h], m);
+                    const float a = (M[h] == -INFINITY) ? 0.f : ex2_approx(M[h] - m_new);
+                    const float b = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new);
+                    L[h] = L[h] * a + l * b;
+                    O[h] = O[h] * a + o * b;
+                    M[h] = m_new;
+                }
+            }
+            const int part = split / p.cluster;                  // index of this cluster among the remaining partials
+            if (d < p.D) {
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const int hq = strm * p.Hq + head * G + h;
+                    if (p.num_splits == p.cluster) {
+                        const float inv = L[h] > 0.f ? 1.0f / L[h] : 0.f;
+                        p.out[(int64_t)hq * p.D + d] = __bfloat16_as_ushort(__float2bfloat16_rn(O[h] * inv));
+                    } else {
+                        p.part_o[((int64_t)part * p.rows_total + hq) * p.D + d] = O[h];
+                        if (d == h) p.part_ml[(int64_t)part * p.rows_total + hq] = make_float2(M[h], L[h]);
+                    }
                 }
             }
         }
-        if (p.num_splits > 1) {
-#pragma unroll
-            for (int h = 0; h < G; ++h)
-                if (row == h) p.part_ml[(int64_t)split * p.rows_total + strm * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
-
-        }
+        cluster_sync_all();                                       // peers keep their shared memory alive until rank 0 has read it
     }
 
     tc_fence_before();
@@ -346,7 +404,28 @@ static int launch_decode_s(const DecMaps& maps, const DecParams& p, dim3 grid, c
         }
         attr_done = true;
     }
-    launch_pdl(PDL_OTHER, attn_decode_kernel<G, SLOTS>, grid, dim3(DEC_THREADS), (size_t)dec_smem(SLOTS), st, maps, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(DEC_THREADS);
+    cfg.dynamicSmemBytes = (size_t)dec_smem(SLOTS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (pdl_enabled(PDL_OTHER)) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    if (p.cluster > 1) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = (unsigned)p.cluster;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, SLOTS>, maps, p);
     return launch_status("attn_decode_kernel");
 }
 
@@ -403,21 +482,38 @@ static int decode_launch_common(const svlm_arena_t* geom, const void* const* are
     }
     p.Hq = q_heads; p.G = G; p.D = D;
     p.kv_len = kv_len; p.num_splits = num_splits;
+    // Splits of one (stream, kv head) that sit in one thread-block cluster merge through distributed shared memory.  Measured on B200
+    // (profiles/r2g_decode_cluster_merge_ab.md): with the few splits of the multi-stream launch (4 per stream and head) the merge
+    // kernel and the fp32 round trip of the partials disappear (22.2 -> 21.2 us for 8 streams x 5.8k keys); clusters of 8 for the
+    // 23-37 splits of a single stream are SLOWER than the separate merge launch (9.8 -> 13.0 us at 5.8k, 27.8 -> 48.2 us at 64k:
+    // rank 0 walks its peers' results serially while they hold their SMs), so that path keeps the merge kernel.
+    // SVLM_DECODE_CLUSTER = 1 / 2 / 4 / 8 overrides the largest cluster size for both.
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("SVLM_DECODE_CLUSTER");
+        forced = e ? atoi(e) : 0;
+        if (forced != 1 && forced != 2 && forced != 4 && forced != 8) forced = 0;
+    }
+    const int max_cluster = forced ? forced : (n_streams > 1 && num_splits <= 4 ? 4 : 1);
+    p.cluster = 1;
+    for (int c = max_cluster; c > 1; c >>= 1)
+        if (num_splits % c == 0) { p.cluster = c; break; }
+    const int n_parts = num_splits / p.cluster;
     p.rows_total = n_streams * q_heads;
     p.kv_head_base = layer * H;
     p.out = (uint16_t*)out;
     p.part_o = (float*)workspace;
-    p.part_ml = num_splits > 1 ? (float2*)((float*)workspace + (size_t)num_splits * p.rows_total * D) : nullptr;
+    p.part_ml = n_parts > 1 ? (float2*)((float*)workspace + (size_t)n_parts * p.rows_total * D) : nullptr;
     p.scale_log2 = scale * 1.4426950408889634f;
 #ifdef SVLM_TRACE
     p.trace = (unsigned long long*)getenv_ptr("SVLM_TRACE_PTR");
 #endif
     if ((rc = launch_decode_g(G, maps, p, dim3(num_splits, H, n_streams), st))) return rc;
-    if (num_splits > 1) {
-        // A separate merge launch beats an in-kernel "last CTA merges" epilogue here (measured: 10.2 vs 12.6 us per layer at
-        // 4k keys, 30.1 vs 33.7 us at 64k): one-head CTAs finish the merge in one load latency.
+    if (n_parts > 1) {
+        // What the clusters left over: a separate merge launch beats an in-kernel "last CTA merges" epilogue here (measured: 10.2 vs
+        // 12.6 us per layer at 4k keys, 30.1 vs 33.7 us at 64k): one-head CTAs finish the merge in one load latency.
         launch_pdl(PDL_OTHER, attn_combine_kernel, dim3(p.rows_total), dim3(128), 0, st, (const float*)p.part_o, (const float2*)p.part_ml, p.out,
-                   p.rows_total, D, num_splits);
+                   p.rows_total, D, n_parts);
         return launch_status("attn_combine_kernel");
     }
     return SVLM_OK;

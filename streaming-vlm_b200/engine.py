@@ -108,6 +108,14 @@ REFERENCE_SAMPLING = GenConfig(do_sample=True, repetition_penalty=1.05, temperat
 PREFILL_BUCKET = 8          # chunk-prefill graphs are captured for token counts rounded up to a multiple of this
 
 
+def decode_split_count(seq_len: int, num_kv_heads: int, limit: int = 1 << 30) -> int:
+    """Split count of the single-stream decode attention for a cache of `seq_len` rows: ~2 key tiles per CTA keeps the serial
+    TMA -> UMMA -> softmax chain short, at most one wave of CTAs (148 SMs / kv heads); the merge kernel takes up to 48 partials in one
+    L2 round trip (swept in benchmarks/microbench.py)."""
+    n_tiles = (seq_len + 128) // 128
+    return max(1, min(limit, 148 // num_kv_heads, -(-n_tiles // 2)))
+
+
 class _GraphCache(OrderedDict):
     """LRU-bounded map of CUDA graphs: the keys carry run-time values (token-count bucket, split count, live buffer,
     generation config), so the number of captured graphs must not grow with the length of the stream."""
@@ -626,8 +634,7 @@ class StreamingEngine:
             raise RuntimeError(f"arena capacity {c.capacity} exceeded during decode")
         # split count for the current cache length: ~2 key tiles per CTA keeps the serial TMA->UMMA->softmax chain short, at most
         # one wave of CTAs; the merge kernel takes up to 48 partials in one L2 round trip (swept in benchmarks/microbench.py)
-        n_tiles = (c.seq_len + 128) // 128
-        self._splits_now = max(1, min(self.decode_splits, 148 // self.geo.num_kv_heads, -(-n_tiles // 2)))
+        self._splits_now = decode_split_count(c.seq_len, self.geo.num_kv_heads, self.decode_splits)
         if self.use_graph:
             key = (c.cur, self._splits_now, self._gen_key(gen))
             gr = self._graphs.get(key)
