@@ -45,6 +45,13 @@ def timed(fn, reps=7, graph=True):
 
 
 def main():
+    from bench import ClockSampler
+    with ClockSampler(0) as clk:
+        sweep()
+    print(json.dumps({"clocks": clk.summary()}), flush=True)
+
+
+def sweep():
     _abi.build()
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
         else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}

@@ -46,6 +46,8 @@ def main():
     sess.args.video_grid_thw = torch.zeros(0, 3, dtype=torch.long, device=dev)
     frames = [synthetic.frames(k).permute(0, 2, 3, 1).contiguous().pin_memory() for k in range(64)]
     lat, t_wall0 = [], time.perf_counter()
+    clk = bench.ClockSampler(0)
+    clk.__enter__()
     for i in range(chunks):
         budget = 20 if fixed else 1 + (i * 7) % 20
         prompt = synthetic.round_prompt(i, time_tokens=8 if fixed else 1 + (i * 5) % 9)
@@ -63,6 +65,10 @@ def main():
                               "prefill_graphs": len(engine._pf_graphs), "decode_graphs": len(engine._graphs), "graph_evictions": engine._pf_graphs.evictions + engine._graphs.evictions,
                               "hbm_allocated_GB": torch.cuda.memory_allocated() / 1e9, "hbm_reserved_GB": torch.cuda.memory_reserved() / 1e9,
                               "compactions": sess.past.compactions, "wall_s": time.perf_counter() - t_wall0}), flush=True)
+    clk.__exit__()
+    print(json.dumps({"summary": True, "chunks": chunks, "wall_s": time.perf_counter() - t_wall0, "p50_chunk_ms_all": 1e3 * statistics.median(lat),
+                      "p50_first_tenth_after_fill_ms": 1e3 * statistics.median(lat[chunks // 10:2 * chunks // 10]) if chunks >= 20 else None,
+                      "p50_last_tenth_ms": 1e3 * statistics.median(lat[-max(chunks // 10, 1):]), "clocks": clk.summary()}), flush=True)
 
 
 def first_step(sess, prompt, frames_thwc, budget):

@@ -62,6 +62,41 @@ if mode == "parity":
     print(json.dumps({"mode": "parity", "rank": rank, "tp": world, "chunks": 12, "tokens": total, "argmax_mismatches_vs_unsharded": mism,
                       "compactions": tp.cache.compactions, "kv_heads_local": local_geo.num_kv_heads, "all_reduces": tp.tp.all_reduces,
                       "cuda_graphs": use_graph}), flush=True)
+elif mode == "kernel":
+    # the fused row-parallel GEMV + one-shot all-reduce + residual kernel on its own, 32B shapes of this TP degree: 64 layers x
+    # (o_proj, down_proj) launches per CUDA-graph replay over distinct weights (>> L2), CUDA events, max over ranks
+    from streaming_vlm_b200 import _abi
+    geo = QWEN25VL_32B
+    ctx = parallel.TpContext(dist.group.WORLD, geo.hidden, max_rows=1024, device=dev)
+    hq, mlp = geo.num_heads * geo.head_dim // world, geo.mlp // world
+    n_l = 24
+    wo = [(torch.randn(geo.hidden, hq, device=dev) * 0.02).to(torch.bfloat16) for _ in range(n_l)]
+    wd = [(torch.randn(geo.hidden, mlp, device=dev) * 0.02).to(torch.bfloat16) for _ in range(n_l)]
+    xo, xd = torch.randn(hq, device=dev).to(torch.bfloat16), torch.randn(mlp, device=dev).to(torch.bfloat16)
+    x = torch.randn(geo.hidden, device=dev).to(torch.bfloat16)
+    res = {}
+    for name, which, ws_, xin in (("o_proj", 0, wo, xo), ("down_proj", 1, wd, xd)):
+        def body():
+            for li in range(n_l):
+                _abi.tp_gemv_allreduce(ctx.ref, which, ws_[li], xin, x, x)
+        body(); torch.cuda.synchronize(); dist.barrier()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            body()
+        gr.replay(); torch.cuda.synchronize(); dist.barrier()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3 / n_l)
+        t = torch.tensor([statistics.median(ts)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wbytes = ws_[0].numel() * 2
+        res[name] = {"us_per_launch": float(t) * 1e6, "weight_bytes_per_rank": wbytes, "hbm_floor_us": wbytes / 6533.8e9 * 1e6,
+                     "frac_of_hbm_floor": wbytes / 6533.8e9 / float(t), "nvlink_bytes_pulled": ctx.nvlink_bytes_per_decode_allreduce(),
+                     "nvlink_floor_us_at_770GBs": ctx.nvlink_bytes_per_decode_allreduce() / 770e9 * 1e6}
+    if rank == 0:
+        print(json.dumps({"mode": "kernel", "geometry": geo.name, "tp": world, "svlm_tp_gemv_allreduce": res}), flush=True)
 else:
     geo = QWEN25VL_32B
     w = synthetic.random_weights(geo, seed=0, device=dev)

@@ -60,8 +60,10 @@ TINY = Geometry("tiny", hidden=512, num_layers=2, num_heads=4, num_kv_heads=2, h
                 vit_depth=4, vit_hidden=320, vit_heads=4, vit_mlp=640, fullatt_block_indexes=(1, 3))
 QWEN25VL_7B = Geometry("qwen2.5-vl-7b", hidden=3584, num_layers=28, num_heads=28, num_kv_heads=4, head_dim=128,
                        mlp=18944)
+# vision tower of the 32B checkpoint: the public 32B / 72B configs carry intermediate_size 3456 (7B: 3420); real checkpoints go
+# through `from_hf_config`, which reads the value from the model's own config
 QWEN25VL_32B = Geometry("qwen2.5-vl-32b", hidden=5120, num_layers=64, num_heads=40, num_kv_heads=8, head_dim=128,
-                        mlp=27648)
+                        mlp=27648, vit_mlp=3456)
 
 PRESETS = {"tiny": TINY, "7b": QWEN25VL_7B, "32b": QWEN25VL_32B}
 

@@ -664,7 +664,7 @@ class StreamingEngine:
         c.seq_len += 1
         c._seen_tokens += 1
 
-    def generate(self, ids_full, pixels, grid, taps=None, forced=None, gen: GenConfig = None, max_new_tokens=None, eos=IM_END):
+    def generate(self, ids_full, pixels, grid, taps=None, forced=None, gen: GenConfig = None, max_new_tokens=None, eos=IM_END, video=None):
         """`model.generate` of the reference for one chunk: ViT + prefill + <= max_new_tokens tokens selected by `gen`
         (default: the engine's own config; `GREEDY` is the parity mode, `REFERENCE_SAMPLING` the reference's).
         `forced` (teacher forcing, the reference's --gt_json idea, inference.py:231-239): token j of the chunk is
@@ -685,7 +685,8 @@ class StreamingEngine:
             self.rng_dev.copy_(self._rng_host, non_blocking=True)
             self._turns += 1
         self._mark("vit_start")
-        video = self.vision_forward(pixels, grid, taps) if pixels is not None else None
+        if video is None:           # (`video`: embeddings of this chunk that the caller already has in flight, see `step`)
+            video = self.vision_forward(pixels, grid, taps) if pixels is not None else None
         if taps is not None and video is not None:
             taps["video_embeds"] = video
         self._mark("prefill_start")
@@ -872,6 +873,11 @@ class StreamingEngine:
         self._mark("step_start")
         if frames is not None:
             pixels, grid = self.ingest(frames)
+        # The vision tower needs nothing but the new frames: with nothing to tap and no section timing asked for, its graph replay
+        # is enqueued FIRST and the host-side eviction planning below (~1 ms) runs while the GPU is busy with it.
+        video = None
+        if pixels is not None and taps is None and not sync_timing:
+            video = self.vision_forward(pixels, grid)
         t0 = time.perf_counter()
         ids, runs = self.begin_step(prompt_ids, grid, previous_text)
         if sync_timing:
@@ -879,7 +885,7 @@ class StreamingEngine:
         t_pkv = time.perf_counter() - t0
 
         t0 = time.perf_counter()
-        seq, n_fwd = self.generate(ids, pixels, grid, taps, forced)
+        seq, n_fwd = self.generate(ids, pixels, grid, taps, forced, video=video)
         if sync_timing:
             torch.cuda.synchronize()
         t_gen = time.perf_counter() - t0

@@ -33,7 +33,9 @@ def test_sass_is_blackwell_native():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
         assert mnemonic in sass, f"{mnemonic} missing: the attention/GEMM kernels must use tcgen05 + TMA"
-    assert "HMMA." not in sass, "legacy mma.sync found"
+    import re
+    assert re.search(r"(?<!UTC)HMMA\.", sass) is None, "legacy mma.sync found"
+    assert "UTCHMMA.2CTA" in sass, "the CTA-pair GEMM must issue tcgen05.mma.cta_group::2"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
