@@ -304,10 +304,13 @@ def kernel_rooflines(engine, pk):
                        for _ in range(4)]) / 4
     out["gemv_norm_lm_head_argmax"] = {"bound": "hbm", "achieved": engine.lm_head.numel() * 2 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "us_per_launch": t * 1e6, "launches_per_step": NEW_TOKENS - 1, "weight_bytes": engine.lm_head.numel() * 2}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
-    except (OSError, KeyError, ValueError):
-        traffic = {}
+    traffic = {}
+    for name in ("r2_traffic.json", "r1_traffic.json"):          # DRAM bytes per launch from the committed ncu --set full captures
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["bytes_per_launch"]
+            break
+        except (OSError, KeyError, ValueError):
+            continue
     for k, v in out.items():
         v["frac"] = v["achieved"] / v["peak"]
         v["traffic"] = traffic.get(k)          # DRAM bytes per launch from the committed ncu --set full capture (or null)

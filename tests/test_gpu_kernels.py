@@ -54,7 +54,11 @@ def make_arena(abi, L, H, cap, seed=0, fill=True):
     a = torch.zeros(2, 3, L, H, cap, 128, dtype=torch.bfloat16)
     if fill:
         a[0] = (torch.randn(3, L, H, cap, 128, generator=g) * 0.5).to(torch.bfloat16)
-    dev = a.to(DEV)
+    # the TMA / UMMA tiles want a 1024-byte aligned base; torch's caching allocator only promises 512 bytes
+    store = torch.zeros(a.numel() + 512, dtype=torch.bfloat16, device=DEV)
+    skip = (-store.data_ptr() % 1024) // 2
+    dev = store[skip:skip + a.numel()].view(a.shape)
+    dev.copy_(a)
     return a, dev, abi.ArenaView(dev)
 
 
