@@ -108,6 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    pdl_wait();          // barriers and TMEM are set up; q, the appended rows and the device-side length come from the predecessor
 
     // ---- work assignment (identical arithmetic in every warp) -------------------------------------
     const int tok0 = m_tile * p.tpt;
@@ -326,6 +327,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
 
         // ---- epilogue: the two halves add their row sums, each stores its 64 output columns ----
+        pdl_trigger();
         asm volatile("bar.sync 1, 256;" ::: "memory");           // every thread is past its last xmax read
         bars->xmax[0][half][row] = l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
 // vectorised; the one-CTA-per-row kernel above would launch 8400 tiny CTAs here (measured 21 us vs ~3 us of traffic).
 __global__ void __launch_bounds__(256) attn_combine_rows_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
                                                                  uint16_t* __restrict__ out, int rows, int D, int num_splits) {
+    pdl_wait();
     const int vec_per_row = D / 4;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)rows * vec_per_row) return;
@@ -484,9 +487,9 @@ static int launch_attn(int mode, const CUtensorMap& tq, const CUtensorMap& tk, c
         attr_done[mode] = true;
     }
     if (mode == MODE_CAUSAL)
-        attn_fwd_kernel<MODE_CAUSAL><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+        launch_pdl(PDL_ELEM, attn_fwd_kernel<MODE_CAUSAL>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, st, tq, tk, tv, p);
     else
-        attn_fwd_kernel<MODE_VARLEN><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+        launch_pdl(PDL_ELEM, attn_fwd_kernel<MODE_VARLEN>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, st, tq, tk, tv, p);
     return launch_status("attn_fwd_kernel");
 }
 
@@ -556,8 +559,8 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
         const int rows = n_q_tokens * q_heads;
         if (num_splits <= 8 && rows >= 256) {
             const int64_t threads = (int64_t)rows * (D / 4);
-            attn_combine_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, rows, D,
-                                                                                                     num_splits);
+            launch_pdl(PDL_ELEM, attn_combine_rows_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                       (const float*)p.part_o, (const float2*)p.part_ml, p.out, rows, D, num_splits);
         } else {
             attn_combine_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(p.part_o, p.part_ml, p.out, rows, D, num_splits);
         }

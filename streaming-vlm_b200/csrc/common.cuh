@@ -52,8 +52,20 @@ inline int launch_status(const char* what) {
 // triggering at kernel START loses 7 ms per chunk (successor CTAs parked at the wait take SM slots from the
 // weight-streaming GEMVs), triggering late gains 2.7-3 % (32.6 -> 33.4 frames/s).
 // SVLM_PDL: 1 = every decode-chain kernel (default), 0 = off, 2 = only the GEMVs, 3 = only attention / merge / finalize
-enum { PDL_GEMV = 1, PDL_OTHER = 2 };
+enum { PDL_GEMV = 1, PDL_OTHER = 2, PDL_ELEM = 4 };
+// PDL_ELEM: the short kernels of the ViT tower and of the chunk prefill (add + RMSNorm, SwiGLU, ViT RoPE, append, embedding splice,
+// prefill / ViT attention and its split merge).  They sit between library GEMMs; SVLM_PDL_ELEM=1 launches them with the attribute
+// (every one of them starts with pdl_wait(), so the switch changes scheduling, never results).
+inline bool pdl_elem_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SVLM_PDL_ELEM");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 inline bool pdl_enabled(int kind) {
+    if (kind == PDL_ELEM) return pdl_elem_enabled();
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SVLM_PDL");

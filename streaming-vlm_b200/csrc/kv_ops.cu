@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(256) qkv_rope_append_kernel(uint16_t* __restri
                                                                uint16_t* __restrict__ q_out, int start, const int32_t* __restrict__ start_dev,
                                                                const int32_t* __restrict__ pos, int pos_stride,
                                                                const int32_t* __restrict__ text_pos_dev, RopeTables tab) {
+    pdl_wait();          // inputs come from the predecessor in the stream (no-op without the launch attribute)
     const int t = blockIdx.x;
     const int lane16 = threadIdx.x & 15;
     const int hw = threadIdx.x >> 4;
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(256) resize_v_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vit_rope_kernel(uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
                                                         const float* __restrict__ sinv, int n_tokens, int heads, int D) {
+    pdl_wait();          // inputs come from the predecessor in the stream (no-op without the launch attribute)
     const int half = D / 2, chunks = half / 8;
     const int64_t total = (int64_t)n_tokens * 2 * heads * chunks;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,6 +468,7 @@ constexpr int RN_MAX_VEC = 8;     // cols <= 128 threads * 8 vectors * 8 element
 __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b,
                                                            const uint16_t* __restrict__ w, uint16_t* __restrict__ out_sum,
                                                            uint16_t* __restrict__ out_norm, int cols, float eps) {
+    pdl_wait();          // inputs come from the predecessor in the stream (no-op without the launch attribute)
     __shared__ float red[4];
     const int64_t base = (int64_t)blockIdx.x * cols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const uint16_t* __rest
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) swiglu_kernel(const uint16_t* __restrict__ gu, uint16_t* __restrict__ out, int rows, int M,
                                                       int64_t gu_stride, int64_t out_stride) {
+    pdl_wait();          // inputs come from the predecessor in the stream (no-op without the launch attribute)
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int vec_per_row = M / 8;
     if (idx >= (int64_t)rows * vec_per_row) return;
@@ -545,6 +549,7 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const uint16_t* __restrict_
 __global__ void __launch_bounds__(128) embed_tokens_kernel(const int64_t* __restrict__ ids, int n, int64_t video_id, int64_t vocab,
                                                             const uint16_t* __restrict__ embed, const uint16_t* __restrict__ video,
                                                             int n_video, int hidden, uint16_t* __restrict__ out, int32_t* __restrict__ status) {
+    pdl_wait();          // inputs come from the predecessor in the stream (no-op without the launch attribute)
     __shared__ int cnt[4];
     const int t = blockIdx.x;
     const int64_t id = ids[t];
@@ -667,9 +672,9 @@ extern "C" int svlm_qkv_rope_append(const svlm_arena_t* arena, int buffer, int l
     RopeTables tab;
     if ((rc = make_tables(&tab, cos_table, sin_table, table_rows, mrope_section_host, arena->head_dim))) return rc;
     ArenaDims ad{arena->layers, arena->kv_heads, arena->head_dim, arena->capacity};
-    qkv_rope_append_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
-        (uint16_t*)arena->base, ad, buffer, layer, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, q_row_stride, k_row_stride,
-        v_row_stride, q_heads, (uint16_t*)q_out, start, start_dev, pos, pos_stride, text_pos_dev, tab);
+    launch_pdl(PDL_ELEM, qkv_rope_append_kernel, dim3(n_tokens), dim3(256), 0, (cudaStream_t)stream, (uint16_t*)arena->base, ad, buffer, layer,
+               (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, q_row_stride, k_row_stride, v_row_stride, q_heads, (uint16_t*)q_out,
+               start, start_dev, pos, pos_stride, text_pos_dev, tab);
     return launch_status("qkv_rope_append_kernel");
 }
 
@@ -750,7 +755,8 @@ extern "C" int svlm_vit_rope(void* qkv, const float* cos, const float* sin, int 
     SVLM_REQUIRE(((uintptr_t)qkv & 15) == 0, "qkv must be 16-byte aligned");
     const int64_t total = (int64_t)n_tokens * 2 * heads * (head_dim / 16);
     if (total == 0) return SVLM_OK;
-    vit_rope_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)qkv, cos, sin, n_tokens, heads, head_dim);
+    launch_pdl(PDL_ELEM, vit_rope_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (uint16_t*)qkv, cos, sin,
+               n_tokens, heads, head_dim);
     return launch_status("vit_rope_kernel");
 }
 
@@ -763,8 +769,8 @@ extern "C" int svlm_add_rmsnorm(const void* a, const void* b, const void* weight
     SVLM_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)weight | (uintptr_t)out_sum | (uintptr_t)out_norm) & 15) == 0,
                  "tensors must be 16-byte aligned");
     if (rows == 0) return SVLM_OK;
-    add_rmsnorm_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)a, (const uint16_t*)b, (const uint16_t*)weight,
-                                                               (uint16_t*)out_sum, (uint16_t*)out_norm, cols, eps);
+    launch_pdl(PDL_ELEM, add_rmsnorm_kernel, dim3(rows), dim3(128), 0, (cudaStream_t)stream, (const uint16_t*)a, (const uint16_t*)b,
+               (const uint16_t*)weight, (uint16_t*)out_sum, (uint16_t*)out_norm, cols, eps);
     return launch_status("add_rmsnorm_kernel");
 }
 
@@ -780,8 +786,8 @@ extern "C" int svlm_swiglu(const void* gate_up, void* out, int rows, int M, int6
     SVLM_REQUIRE((((uintptr_t)gate_up | (uintptr_t)out) & 15) == 0, "tensors must be 16-byte aligned");
     const int64_t total = (int64_t)rows * (M / 8);
     if (total == 0) return SVLM_OK;
-    swiglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)gate_up, (uint16_t*)out, rows, M,
-                                                                                     gate_up_row_stride, out_row_stride);
+    launch_pdl(PDL_ELEM, swiglu_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const uint16_t*)gate_up,
+               (uint16_t*)out, rows, M, gate_up_row_stride, out_row_stride);
     return launch_status("swiglu_kernel");
 }
 
@@ -794,8 +800,8 @@ extern "C" int svlm_embed_tokens(const int64_t* ids, int n_tokens, int64_t video
     SVLM_REQUIRE(hidden > 0 && hidden % 8 == 0, "hidden %d must be a positive multiple of 8", hidden);
     SVLM_REQUIRE((((uintptr_t)embed | (uintptr_t)video | (uintptr_t)out) & 15) == 0, "embed / video / out must be 16-byte aligned");
     if (n_tokens == 0) return SVLM_OK;
-    embed_tokens_kernel<<<n_tokens, 128, 0, (cudaStream_t)stream>>>(ids, n_tokens, video_token_id, vocab, (const uint16_t*)embed,
-                                                                   (const uint16_t*)video, n_video, hidden, (uint16_t*)out, status);
+    launch_pdl(PDL_ELEM, embed_tokens_kernel, dim3(n_tokens), dim3(128), 0, (cudaStream_t)stream, ids, n_tokens, (int64_t)video_token_id,
+               (int64_t)vocab, (const uint16_t*)embed, (const uint16_t*)video, n_video, hidden, (uint16_t*)out, status);
     return launch_status("embed_tokens_kernel");
 }
 

@@ -151,7 +151,10 @@ def test_padded_prefill_graphs_and_variable_turns_stay_bounded():
     """Chunk-prefill graphs are keyed on a token-count BUCKET (padded tail rows, device-side true length) and both graph caches are
     LRU-bounded: a stream whose turns end after 1..20 tokens and whose prompts vary in length (1..9 time tokens) must (a) give
     the same stream as exact-length prefills, (b) keep the number of captured graphs and the allocated HBM flat."""
+    import gc
     from streaming_vlm_b200.engine import IM_END, StreamingEngine
+    gc.collect()                                # engines of earlier tests must not be freed in the middle of the HBM-flatness window
+    torch.cuda.synchronize()
     geo = TINY
     w_cpu = synthetic.random_weights(geo, seed=0)
     suppress = torch.ones(geo.vocab, dtype=torch.bool)
