@@ -389,6 +389,39 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     byt = sum(c.seq_len for c in caches) * 2 * g.num_kv_heads * g.head_dim * 2
     out["attn_decode_streams"] = {"bound": "hbm", "achieved": byt / ta / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byt / ta / 1e9 / pk["hbm_gbs"],
                                   "us_per_launch": ta * 1e6, "splits": splits, "alg_bytes_per_launch": byt}
+    # the chunk-prefill attention of all streams the way the batched prefill runs it: one un-split launch per stream, the streams'
+    # launches side by side on their own CUDA streams (fork / join inside the graph), Tq = 300 new tokens each
+    tq = 300
+    qp = torch.randn(n_streams * tq, g.num_heads, g.head_dim, device=dev).to(torch.bfloat16)
+    op = torch.empty_like(qp)
+
+    def pre():
+        main = torch.cuda.current_stream()
+        for li in range(L):
+            for b, c in enumerate(caches):
+                side = multi._pf_streams[b]
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    _abi.attn_causal(c.view, c.cur, li, qp[b * tq:(b + 1) * tq], op[b * tq:(b + 1) * tq], tq, g.num_heads, c.seq_len, multi.engines[0].scale, 1, None)
+            for b in range(n_streams):
+                main.wait_stream(multi._pf_streams[b])
+    pre()
+    torch.cuda.synchronize()
+    gr2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr2):
+        pre()
+    gr2.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); gr2.replay(); a1.record(); torch.cuda.synchronize()
+        ts.append(a0.elapsed_time(a1) * 1e-3 / L)
+    tp_ = statistics.median(ts)
+    fl = sum(4.0 * tq * (c.seq_len - tq / 2) * g.head_dim * g.num_heads for c in caches)
+    out["attn_prefill_streams"] = {"bound": "tensor", "achieved": fl / tp_ / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": fl / tp_ / 1e12 / pk["bf16_burst"],
+                                   "us_per_layer_all_streams": tp_ * 1e6, "tq": tq, "alg_flop_per_layer": fl,
+                                   "note": "8 un-split launches per layer, one per stream, concurrent on 8 CUDA streams"}
     return out
 
 

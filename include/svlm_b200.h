@@ -292,13 +292,15 @@ int svlm_frames_resize_bicubic(const void* in_thwc_u8, int n_frames, int height,
  * NCCL all-reduce + a residual-add kernel per projection, the partial sums go to a buffer in SYMMETRIC memory (same allocation
  * on every rank, every rank has every peer's copy mapped: torch.distributed._symmetric_memory or cuMem fabric handles) and the
  * reduction is a one-shot exchange over NVLink loads inside our own kernels -- no NCCL call, CUDA-graph capturable:
- *   svlm_tp_gemv_allreduce : decode step.  y = residual + bf16(sum_r W_r x_r): each CTA streams its rows of W (bf16 [N][K_local]),
- *       writes fp32 partial sums into this rank's region; the CTA that finishes last announces the epoch to all peers (release
- *       store into their flag arrays), waits for theirs, sums the W partial vectors in rank order, adds the residual, writes y.
+ *   svlm_tp_gemv_allreduce : decode step.  y = residual + bf16(sum_r W_r x_r): each CTA streams its rows of W (bf16 [N][K_local])
+ *       and PUSHES its fp32 partial sums to every rank's region as 8-byte (value, epoch) words (NVLink stores; the epoch travels
+ *       with the value, so there is no flag, fence or round trip); the CTA that finishes last waits until the words of all ranks
+ *       carry this epoch, sums the W partial vectors in rank order, adds the residual, writes y.
  *   svlm_tp_allreduce_rows : chunk prefill.  The partial products [rows][cols] bf16 were written into this rank's region by the
  *       GEMM (svlm_tp_ctx_t offsets below); out = residual + bf16(sum_r part_r).
  * Symmetric buffer layout (bytes, identical on every rank):  [0, 1024) flag words (uint32 per peer rank), then two regions of
- * `region_bytes` for decode partials (fp32 [N]: which = 0 attention output, 1 MLP output) at SVLM_TP_DECODE_OFFSET, then two
+ * `region_bytes` for decode partials ([source rank][N] x (fp32 value, uint32 epoch): which = 0 attention output, 1 MLP output) at
+ * SVLM_TP_DECODE_OFFSET, then two
  * regions of `region_bytes` for row partials (bf16 [rows][cols]) behind them.  Two regions (`which`) are what makes reuse safe
  * without a trailing barrier: a region is rewritten only after every peer has passed the NEXT all-reduce.
  * `seq` / `done`: two zero-initialised uint32 in LOCAL device memory owned by the context. */

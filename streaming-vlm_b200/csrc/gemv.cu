@@ -44,6 +44,15 @@ __device__ __forceinline__ uint4 ld_relaxed_sys_u4(const void* p) {
     return v;
 }
 
+__device__ __forceinline__ void st_relaxed_sys_u2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_u4_v(const void* p) {      // two (value, epoch) words
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // Cross-rank rendezvous of one all-reduce, executed by ONE CTA per rank once this rank's partial sums are complete and visible:
 // announce epoch = *seq + 1 to every peer (release store into the peer's flag array over NVLink), then wait until every peer has
 // announced the same epoch to us.  A rank that never shows up turns into a trap after ~2 s instead of a hung GPU.
@@ -323,7 +332,14 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
                     p.scores_out[n] = -INFINITY;
                 }
             } else if (MODE == GEMV_TP) {
-                p.tp_part[n] = v;                                                  // fp32 partial sum of this rank's K slice
+                // fp32 partial sum of this rank's K slice, PUSHED to every rank (NVLink stores, fire and forget) as an 8-byte
+                // (value, epoch) word: the epoch travels with the value, so the receiver needs no separate flag, fence or round trip
+                const uint32_t epoch = *p.tp.seq + 1u;
+#pragma unroll
+                for (int r = 0; r < SVLM_MAX_TP; ++r)
+                    if (r < p.tp.world)
+                        st_relaxed_sys_u2(reinterpret_cast<uint2*>(const_cast<void*>(p.tp.peer_part[r])) + (size_t)p.tp.rank * p.N + n,
+                                          __float_as_uint(v), epoch);
             } else if (MODE == GEMV_SWIGLU) {
                 const float gt = round_bf16(v), up = round_bf16(v2);
                 const float sl = round_bf16(gt / (1.0f + __expf(-gt)));
@@ -346,9 +362,9 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
         }
     }
     if (MODE == GEMV_TP) {
-        // The CTA that finishes last owns the all-reduce: every other CTA's partial sums are visible to it (fence + counter),
-        // it meets the peer ranks, sums the W partial vectors in rank order (the same order on every rank: bit-identical
-        // results everywhere), rounds to bf16 like the unsharded Linear does, adds the residual and writes y.
+        // The CTA that finishes last owns the reduction: it waits until the words of all ranks (its own included) carry this epoch,
+        // sums the W partial vectors in rank order (the same order on every rank: bit-identical results everywhere), rounds to
+        // bf16 like the unsharded Linear does, adds the residual and writes y.  One-way NVLink latency is all that is exposed.
         __shared__ int is_last;
         __syncthreads();
         if (t == 0) {
@@ -358,22 +374,32 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
         }
         __syncthreads();
         if (!is_last) return;
-        const uint32_t epoch = tp_rendezvous(p.tp);
-        for (int n = t * 4; n < p.N; n += GEMV_THREADS * 4) {
-            float4 part[SVLM_MAX_TP];
+        // every rank's words land in THIS rank's buffer ([source rank][N] x (value, epoch)); a word is valid once its epoch matches
+        const uint32_t epoch = *p.tp.seq + 1u;
+        const uint2* mine = reinterpret_cast<const uint2*>(p.tp.peer_part[p.tp.rank]);
+        const long long t0 = clock64();
+        for (int n = t * 2; n < p.N; n += GEMV_THREADS * 2) {
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int r = 0; r < SVLM_MAX_TP; ++r)
-                if (r < p.tp.world) part[r] = ld_relaxed_sys_f4(reinterpret_cast<const float*>(p.tp.peer_part[r]) + n);
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < SVLM_MAX_TP; ++r)
-                if (r < p.tp.world) { sum.x += part[r].x; sum.y += part[r].y; sum.z += part[r].z; sum.w += part[r].w; }
-            const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + n);
-            uint2 o;
-            o.x = pack_bf16(round_bf16(sum.x) + bf16_lo(rv.x), round_bf16(sum.y) + bf16_hi(rv.x));
-            o.y = pack_bf16(round_bf16(sum.z) + bf16_lo(rv.y), round_bf16(sum.w) + bf16_hi(rv.y));
-            *reinterpret_cast<uint2*>(p.y + n) = o;
+            for (int r = 0; r < SVLM_MAX_TP; ++r) {
+                if (r < p.tp.world) {
+                    const uint2* src = mine + (size_t)r * p.N + n;
+                    uint4 w = ld_relaxed_sys_u4_v(src);
+                    while (w.y != epoch || w.w != epoch) {
+                        if (clock64() - t0 > 4000000000ll) {
+                            printf("svlm: tensor-parallel all-reduce timed out (rank %d waiting for rank %d, epoch %u, row %d)\n", p.tp.rank, r, epoch, n);
+                            __trap();
+                        }
+                        w = ld_relaxed_sys_u4_v(src);
+                    }
+                    s0 += __uint_as_float(w.x);
+                    s1 += __uint_as_float(w.z);
+                }
+            }
+            const uint32_t rv = *reinterpret_cast<const uint32_t*>(p.residual + n);
+            *reinterpret_cast<uint32_t*>(p.y + n) = pack_bf16(round_bf16(s0) + bf16_lo(rv), round_bf16(s1) + bf16_hi(rv));
         }
+        __syncthreads();
         if (t == 0) { *p.tp.seq = epoch; *p.tp.done = 0u; }
     }
 }
@@ -654,9 +680,9 @@ extern "C" int svlm_tp_gemv_allreduce(const svlm_tp_ctx_t* ctx, int which, const
     int rc = check_device();
     if (rc) return rc;
     if ((rc = gemv_common_checks(W, x, y, N, K))) return rc;
-    SVLM_REQUIRE(residual != nullptr && N % 4 == 0, "residual is NULL or N %d is not a multiple of 4", N);
+    SVLM_REQUIRE(residual != nullptr && N % 2 == 0, "residual is NULL or N %d is odd", N);
     GemvParams p{(const uint16_t*)W, (const uint16_t*)x, nullptr, 0.f, nullptr, (const uint16_t*)residual, (uint16_t*)y, N, K, nullptr, nullptr};
-    if ((rc = make_tp_dev(ctx, which, SVLM_TP_DECODE_OFFSET, (size_t)N * sizeof(float), &p.tp))) return rc;
+    if ((rc = make_tp_dev(ctx, which, SVLM_TP_DECODE_OFFSET, (size_t)ctx->world * N * 8, &p.tp))) return rc;
     p.tp_part = const_cast<float*>(reinterpret_cast<const float*>(p.tp.peer_part[ctx->rank]));
     return dispatch_shape<GEMV_TP, false>(p, (cudaStream_t)stream);
 }

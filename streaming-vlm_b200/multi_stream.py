@@ -19,6 +19,8 @@ Results per stream are those of the single-stream engine up to the GEMM-vs-GEMV 
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import time
 
 import torch
@@ -62,6 +64,8 @@ class MultiStreamEngine:
         self._pf_graphs, self._pf_seen, self._pf_calls = {}, {}, 0
         self._pf_ids = torch.zeros(B * 1024, dtype=torch.int64, device=dev)
         self.batch_prefill = True      # ViT and chunk prefill of all streams in one pass (one weight sweep); False = per stream
+        self.concurrent_prefill = os.environ.get("SVLM_CONCURRENT_PREFILL", "1") != "0"   # per-stream append + attention on side streams
+        self._pf_streams = [torch.cuda.Stream(device=dev) for _ in range(B)]
         self.use_graph = first.use_graph
         self.launches = 0
         self.timing = []
@@ -153,13 +157,29 @@ class MultiStreamEngine:
             q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
             q_rot = torch.empty(total, hq, d, dtype=torch.bfloat16, device=self.device)
             o = torch.empty(total, hq, d, dtype=torch.bfloat16, device=self.device)
-            for e, (off, t, _, splits) in zip(self.engines, metas):
+            # Append + attention of the streams are independent of each other (own arena, own rows of q / o): they fork onto one side
+            # stream per stream and run CONCURRENTLY, each as ONE launch over the whole KV range (no split, no merge kernel) -- a
+            # single stream's 68 CTAs leave half of the SMs idle and need a 2-way split + merge to fill them; two streams side by side
+            # fill them with full-length chains (the regime in which this kernel reaches 0.55 of the tensor peak).  Inside a CUDA-graph
+            # capture the fork / join becomes graph edges.
+            main = torch.cuda.current_stream()
+            concurrent = self.concurrent_prefill and len(self.engines) > 1
+            for b, (e, (off, t, _, splits)) in enumerate(zip(self.engines, metas)):
                 c, sl = e.cache, slice(off, off + t)
-                _abi.qkv_rope_append(c.view, c.cur, li, q[sl], k[sl], v[sl], t, hq, q_rot[sl], 0, c.pos, c.cos_table, c.sin_table, c.section,
-                                     start_dev=e.kv_len_dev)
-                _abi.attn_causal(c.view, c.cur, li, q_rot[sl], o[sl], t, hq, c.capacity, e.scale, splits, e.ws if splits > 1 else None,
-                                 kv_len_dev=e.kv_after_dev)
+                if concurrent:
+                    side = self._pf_streams[b]
+                    side.wait_stream(main)
+                    splits = 1
+                ctx = torch.cuda.stream(side) if concurrent else contextlib.nullcontext()
+                with ctx:
+                    _abi.qkv_rope_append(c.view, c.cur, li, q[sl], k[sl], v[sl], t, hq, q_rot[sl], 0, c.pos, c.cos_table, c.sin_table, c.section,
+                                         start_dev=e.kv_len_dev)
+                    _abi.attn_causal(c.view, c.cur, li, q_rot[sl], o[sl], t, hq, c.capacity, e.scale, splits, e.ws if splits > 1 else None,
+                                     kv_len_dev=e.kv_after_dev)
                 self.launches += 2 + (1 if splits > 1 else 0)
+            if concurrent:
+                for b in range(len(self.engines)):
+                    main.wait_stream(self._pf_streams[b])
             x, h = e0._add_norm(x, F.linear(o.view(total, -1), L["wo"]), L["ln2"], g.rms_eps)
             pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
         logits = e0._logits(x[last], pending[last])           # `last`: row of the last new token of every stream

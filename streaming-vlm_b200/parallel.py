@@ -83,7 +83,7 @@ class TpContext:
             raise ValueError(f"tensor-parallel degree must be 2..{_abi.MAX_TP}, got {self.world}")
         dev = torch.device(device if device is not None else torch.cuda.current_device())
         self.hidden, self.max_rows = hidden, max_rows
-        self.region = -(-max(hidden * 4, max_rows * hidden * 2) // 1024) * 1024
+        self.region = -(-max(self.world * hidden * 8, max_rows * hidden * 2) // 1024) * 1024
         nbytes = _abi.TP_DECODE_OFFSET + 4 * self.region
         self.buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
         self.handle = symm.rendezvous(self.buf, group)
@@ -113,5 +113,5 @@ class TpContext:
         return self.buf[off:off + rows * cols * 2].view(torch.bfloat16).view(rows, cols)
 
     def nvlink_bytes_per_decode_allreduce(self):
-        """Bytes this rank pulls over NVLink in one decode all-reduce: (world - 1) peers x hidden fp32 partial sums."""
-        return (self.world - 1) * self.hidden * 4
+        """Bytes this rank pushes over NVLink in one decode all-reduce: (world - 1) peers x hidden (fp32 value, epoch) words."""
+        return (self.world - 1) * self.hidden * 8
