@@ -167,6 +167,25 @@ int svlm_gemm_bf16(const void* A, const void* W, const void* bias, void* C, int 
  *   tile_n: 0 = chosen per shape from the measured UMMA costs, or 64 / 128 / 256 to force a tile width. */
 int svlm_gemm_bf16_ex(const void* A, const void* W, const void* bias, const void* residual, void* C, int M, int N, int K,
                       int epilogue, const int32_t* out_rows, int tile_n, void* stream);
+/* "Few tokens x whole weight matrix": Y[T][N] = epilogue(X[T][K] W^T + bias), 1 <= T <= 64.  The dense projections of the BATCHED decode
+ * step (one token per stream, T = streams; the same nn.Linear call sites as above executed for a [T, hidden] activation matrix) are
+ * weight streams: the weight rows are the tensor-core M dimension (swap-AB, 128-row TMA panels), the tokens the N dimension
+ * (16 / 32 / 64 TMEM columns); small N is split along K over a thread-block cluster whose partial tiles are reduced through
+ * distributed shared memory in rank order (deterministic, no workspace).  One launch per projection:
+ *   epilogue 0: Y = bf16(X W^T + bias)                      (q/k/v projection, lm_head)
+ *   epilogue 2: Y = bf16(bf16(X W^T + bias) + residual)     (o_proj / down_proj + `hidden = residual + x`; residual [T][N], may alias Y)
+ *   epilogue 3: SwiGLU: W = [gate rows ; up rows] (N = 2 * width, plain concatenation), Y [T][N/2] = bf16(silu(bf16 gate)) * bf16 up
+ *   splits: 0 = chosen per shape (~1.5 CTAs per SM), else 1..8 CTAs per cluster along K.
+ *   norm_weight (bf16 [K]) / eps: non-NULL = X is RMS-normalised on the fly (HF Qwen2RMSNorm in front of q/k/v, gate/up, lm_head;
+ *       row statistics and rounding points identical to svlm_add_rmsnorm): the epilogue warps normalise every X panel in shared
+ *       memory while the weight ring streams -- no norm launch, no normalised copy of X.
+ *   stats_out (fp32 [ceil(N / 128)][T], epilogue 0 / 2, T <= 16) or NULL: the sum of squares of the 128 values of every token that each
+ *       row tile wrote -- what the NEXT RMSNorm needs of Y.  stats_in / stats_tiles: such a table for X, left by the launch that
+ *       produced X (o_proj -> post-attention norm, down_proj -> next layer's input norm): the row statistics then cost one short read
+ *       instead of a pass over X in every CTA; NULL = computed from X in the kernel. */
+int svlm_gemm_tokens(const void* X, const void* W, const void* bias, const void* residual, void* Y, int T, int N, int K,
+                     int epilogue, int splits, const void* norm_weight, float eps, const float* stats_in, int stats_tiles,
+                     float* stats_out, void* stream);
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -263,6 +282,16 @@ int svlm_qkv_rope_append_streams(const svlm_arena_t* geometry, const svlm_stream
 int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
                              const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
                              size_t workspace_bytes, float scale, void* stream);
+/* The q/k/v projection of the batched decode step with everything around it in ONE launch (replaces svlm_add_rmsnorm + GEMM + bias +
+ * svlm_qkv_rope_append_streams; reference: input_layernorm + q/k/v_proj + apply_multimodal_rotary_pos_emb + cache update,
+ * language_forward.py:47-66, 175-192, generate/streaming_cache.py:72-73): X [n_streams][hidden] is normalised (norm_weight, eps),
+ * multiplied with W [(q_heads + 2 kv_heads) * 128][hidden] (+ bias); a 128-row output tile is one head, which the epilogue rotates
+ * at text position *slots[b].pos_dev (all three mRoPE axes) and writes to q_rot [n_streams][q_heads][128] resp. to the K_raw / K_rot /
+ * V planes of stream b's arena at row *slots[b].row_dev.  cos / sin tables as in svlm_qkv_rope_append; stats_in as in svlm_gemm_tokens. */
+int svlm_gemm_tokens_qkv_append(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
+                                const void* X, const void* W, const void* bias, const void* norm_weight, float eps,
+                                const float* stats_in, int stats_tiles, int q_heads, int hidden, void* q_rot,
+                                const void* cos_table, const void* sin_table, int table_rows, int splits, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (9) Frame ingest ("next" row f3).  Replaces the pixel half of `processor(text=..., videos=clip)`

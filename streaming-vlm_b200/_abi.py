@@ -16,13 +16,13 @@ import torch
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libsvlm_b200.so")
-SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "attn_decode.cu", "gemm.cu", "gemv.cu"]
+SOURCES = ["abi.cu", "kv_ops.cu", "attn_fwd.cu", "attn_decode.cu", "gemm.cu", "gemm_tokens.cu", "gemv.cu"]
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "svlm_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-rdc=false",
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
-           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex",
+           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex", "svlm_gemm_tokens", "svlm_gemm_tokens_qkv_append",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
            "svlm_frames_to_patches", "svlm_frames_resize_bicubic", "svlm_tp_gemv_allreduce", "svlm_tp_allreduce_rows",
            "svlm_kv_compact_rope_host"]
@@ -99,6 +99,9 @@ def lib() -> ctypes.CDLL:
     L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
     L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
     L.svlm_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, c_int, vp]
+    L.svlm_gemm_tokens.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, c_float, vp, c_int, vp, vp]
+    L.svlm_gemm_tokens_qkv_append.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, vp, c_float, vp, c_int, c_int, c_int,
+                                              vp, vp, vp, c_int, c_int, vp]
     L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_swiglu.argtypes = [vp, vp, c_int, c_int, c_int64, c_int64, vp]
@@ -242,6 +245,39 @@ def gemm_ex(a, w, out, bias=None, residual=None, epilogue: int = EPI_NONE, out_r
     assert out.shape[1] == (n // 2 if epilogue == EPI_SWIGLU else n)
     check(lib().svlm_gemm_bf16_ex(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), m, n, k, epilogue, _ptr(out_rows),
                                   tile_n, _stream()), "svlm_gemm_bf16_ex")
+
+
+def gemm_tokens(x, w, out, bias=None, residual=None, epilogue: int = EPI_NONE, splits: int = 0, norm_weight=None, eps: float = 1e-6,
+                stats_in=None, stats_out=None):
+    """out[T, N] = epilogue(norm(x)[T, K] @ w.T + bias) for T <= 64 tokens: the weight-streaming swap-AB GEMM of the batched decode step
+    (include/svlm_b200.h, svlm_gemm_tokens).  epilogue EPI_SWIGLU takes w = [gate rows ; up rows] and writes [T, N / 2];
+    `norm_weight`: RMSNorm of x fused into the kernel; `stats_out` (fp32 [ceil(N / 128), T]): per-tile sums of squares of the rows
+    written, `stats_in`: such a table for x, left by the launch that produced it."""
+    _req_cuda(x, w, out, bias, residual, norm_weight, stats_in, stats_out)
+    assert stats_in is None or (stats_in.dtype == torch.float32 and stats_in.is_contiguous() and stats_in.shape[1] == x.shape[0])
+    assert stats_out is None or (stats_out.dtype == torch.float32 and stats_out.is_contiguous()
+                                 and tuple(stats_out.shape) == (-(-w.shape[0] // 128), x.shape[0]))
+    t, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and x.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    assert tuple(out.shape) == (t, n // 2 if epilogue == EPI_SWIGLU else n)
+    assert residual is None or (residual.is_contiguous() and residual.shape == out.shape)
+    check(lib().svlm_gemm_tokens(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), t, n, k, epilogue, splits,
+                                 _ptr(norm_weight), eps, _ptr(stats_in), 0 if stats_in is None else stats_in.shape[0], _ptr(stats_out),
+                                 _stream()), "svlm_gemm_tokens")
+
+
+def gemm_tokens_qkv_append(geometry: "ArenaView", slots, layer, x, w, bias, norm_weight, eps, q_heads, q_rot, cos_table, sin_table,
+                           splits: int = 0, stats_in=None):
+    """Batched decode step: RMSNorm + q/k/v projection + bias + mRoPE + arena append of token b into stream b, one launch
+    (include/svlm_b200.h, svlm_gemm_tokens_qkv_append)."""
+    _req_cuda(x, w, bias, norm_weight, q_rot, stats_in)
+    assert x.is_contiguous() and w.is_contiguous() and q_rot.is_contiguous() and x.shape[0] == len(slots)
+    assert stats_in is None or (stats_in.dtype == torch.float32 and stats_in.is_contiguous() and stats_in.shape[1] == x.shape[0])
+    check(lib().svlm_gemm_tokens_qkv_append(geometry.ref, slots, len(slots), layer, x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(norm_weight),
+                                            eps, _ptr(stats_in), 0 if stats_in is None else stats_in.shape[0], q_heads, x.shape[1],
+                                            q_rot.data_ptr(), cos_table.data_ptr(), sin_table.data_ptr(),
+                                            cos_table.shape[0], splits, _stream()), "svlm_gemm_tokens_qkv_append")
 
 
 def interleave_gate_up(gate, up, block: int = 64):

@@ -178,6 +178,21 @@ __device__ __forceinline__ uint64_t ex2_poly2(uint64_t x) {
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// HF RMSNorm statistics with a FIXED operation order (explicit roundings, no contraction), shared by add_rmsnorm_kernel and the
+// fused RMSNorm prologue of gemm_tokens_kernel so that both produce bit-identical rstd values.
+__device__ __forceinline__ float sumsq8(float ss, const uint4& v) {
+    const uint32_t* p = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float x0 = bf16_lo(p[k]), x1 = bf16_hi(p[k]);
+        ss = __fadd_rn(ss, __fmaf_rn(x1, x1, __fmul_rn(x0, x0)));
+    }
+    return ss;
+}
+__device__ __forceinline__ float rms_rstd(float w0, float w1, float w2, float w3, int cols, float eps) {
+    return rsqrtf(__fadd_rn(__fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(w0, w1), w2), w3), (float)cols), eps));
+}
+
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));

@@ -487,16 +487,14 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const uint16_t* __rest
                 for (int k = 0; k < 4; ++k) p[k] = pack_bf16(bf16_lo(p[k]) + bf16_lo(q[k]), bf16_hi(p[k]) + bf16_hi(q[k]));
                 if (out_sum) *reinterpret_cast<uint4*>(out_sum + base + c) = v[i];
             }
-            const uint32_t* p = &v[i].x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float x0 = bf16_lo(p[k]), x1 = bf16_hi(p[k]); ss += x0 * x0 + x1 * x1; }
+            ss = sumsq8(ss, v[i]);
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
     if (lane == 0) red[warp] = ss;
     __syncthreads();
-    const float r = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)cols + eps);
+    const float r = rms_rstd(red[0], red[1], red[2], red[3], cols, eps);
 #pragma unroll
     for (int i = 0; i < RN_MAX_VEC; ++i) {
         const int c = (i * 128 + threadIdx.x) * 8;
@@ -508,7 +506,8 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const uint16_t* __rest
             uint32_t* po = &o.x;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                po[k] = pack_bf16(bf16_lo(q[k]) * round_bf16(bf16_lo(p[k]) * r), bf16_hi(q[k]) * round_bf16(bf16_hi(p[k]) * r));
+                po[k] = pack_bf16(__fmul_rn(bf16_lo(q[k]), round_bf16(__fmul_rn(bf16_lo(p[k]), r))),
+                                  __fmul_rn(bf16_hi(q[k]), round_bf16(__fmul_rn(bf16_hi(p[k]), r))));
             *reinterpret_cast<uint4*>(out_norm + base + c) = o;
         }
     }

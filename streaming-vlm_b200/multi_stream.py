@@ -66,6 +66,7 @@ class MultiStreamEngine:
         self.batch_prefill = True      # ViT and chunk prefill of all streams in one pass (one weight sweep); False = per stream
         self.concurrent_prefill = os.environ.get("SVLM_CONCURRENT_PREFILL", "1") != "0"   # per-stream append + attention on side streams
         self._pf_streams = [torch.cuda.Stream(device=dev) for _ in range(B)]
+        self.own_gemm = os.environ.get("SVLM_BATCHED_DECODE_CUBLAS", "0") != "1"      # decode projections: svlm_gemm_tokens (default) / cuBLAS
         self.use_graph = first.use_graph
         self.launches = 0
         self.timing = []
@@ -77,6 +78,46 @@ class MultiStreamEngine:
         c0 = e0.cache
         before = e0.launches
         x = F.embedding(self.tok, e0.embed)
+        if not self.own_gemm:
+            return self._decode_body_cublas(x, slots, splits, before)
+        # Five launches per layer, every projection ONE launch of the weight-streaming swap-AB GEMM (svlm_gemm_tokens: weight rows on
+        # the tensor-core M dimension, the B tokens on N, split-K over a cluster) with everything around it fused:
+        #   RMSNorm -> q/k/v projection -> bias -> mRoPE -> append to each stream's arena | split-KV attention over all streams |
+        #   o_proj + residual | RMSNorm -> gate/up projection -> SwiGLU | down_proj + residual;   final norm -> lm_head.
+        # The two row-parallel launches leave per-tile sums of squares of the rows they wrote (`stats`), from which the NEXT launch's
+        # fused RMSNorm gets its row statistics with one short read (layer 0 computes them from the embedding rows in the kernel).
+        dev, bf = self.device, torch.bfloat16
+        act = torch.empty(B, g.mlp, dtype=bf, device=dev)
+        st_attn = torch.empty(-(-g.hidden // 128), B, dtype=torch.float32, device=dev)
+        st_mlp = torch.empty_like(st_attn)
+        for li, L in enumerate(e0.layers):
+            _abi.gemm_tokens_qkv_append(c0.view, slots, li, x, L["wqkv"], L["bqkv"], L["ln1"], g.rms_eps, hq, self._q_rot, c0.cos_table,
+                                        c0.sin_table, stats_in=st_mlp if li else None)
+            _abi.attn_decode_streams(c0.view, slots, li, self._q_rot, self._o, hq, c0.capacity, e0.scale, splits,
+                                     self.ws if splits > 1 else None)
+            _abi.gemm_tokens(self._o.view(B, -1), L["wo"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_attn)
+            _abi.gemm_tokens(x, L["wgu"], act, epilogue=_abi.EPI_SWIGLU, norm_weight=L["ln2"], eps=g.rms_eps, stats_in=st_attn)
+            _abi.gemm_tokens(act, L["wd"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_mlp)
+        logits = torch.empty(B, e0.lm_head.shape[0], dtype=bf, device=dev)
+        _abi.gemm_tokens(x, e0.lm_head, logits, norm_weight=e0.norm, eps=g.rms_eps, stats_in=st_mlp)
+        logits = logits.float()
+        if e0.suppress is not None:
+            logits = logits.masked_fill(e0.suppress, float("-inf"))
+        self.launches += g.num_layers * (5 + (1 if splits > 1 else 0)) + 1
+        self._advance(torch.argmax(logits, dim=-1))
+
+    def _advance(self, nxt):
+        act = self.active
+        self.tok.copy_(torch.where(act.bool(), nxt, self.tok))
+        self.kv_len.add_(act)
+        self.kv_after.copy_(self.kv_len + 1)
+        self.next_pos.add_(act)
+
+    def _decode_body_cublas(self, x, slots, splits, before):
+        """The same step with the projections in cuBLAS (SVLM_BATCHED_DECODE_CUBLAS=1: the A/B baseline of the own kernels)."""
+        e0, g, B = self.engines[0], self.geo, self.n
+        hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
+        c0 = e0.cache
         pending = None
         for li, L in enumerate(e0.layers):
             x, h = e0._add_norm(x, pending, L["ln1"], g.rms_eps)
@@ -88,12 +129,7 @@ class MultiStreamEngine:
             x, h = e0._add_norm(x, F.linear(self._o.view(B, -1), L["wo"]), L["ln2"], g.rms_eps)
             pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
         logits = e0._logits(x, pending)                                   # [B, vocab] fp32, suppressed ids at -inf
-        nxt = torch.argmax(logits, dim=-1)
-        act = self.active
-        self.tok.copy_(torch.where(act.bool(), nxt, self.tok))
-        self.kv_len.add_(act)
-        self.kv_after.copy_(self.kv_len + 1)
-        self.next_pos.add_(act)
+        self._advance(torch.argmax(logits, dim=-1))
         self.launches += (e0.launches - before) + g.num_layers * (2 + (1 if splits > 1 else 0))
         e0.launches = before
 

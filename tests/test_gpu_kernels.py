@@ -731,3 +731,183 @@ def test_gemm_ex_swiglu(abi, m, width, k):
     out = torch.empty(m, width, dtype=torch.bfloat16, device=DEV)
     abi.gemm_ex(a.to(DEV), w, out, epilogue=abi.EPI_SWIGLU)
     torch.testing.assert_close(out.cpu().float(), want.float(), rtol=2e-2, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# svlm_gemm_tokens: few tokens x whole weight matrix (swap-AB tcgen05, split-K over a cluster), the batched decode step's projections
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t,n,k,splits", [
+    (8, 4608, 3584, 0), (8, 3584, 3584, 0), (8, 3584, 18944, 0),          # 7B q/k/v, o_proj, down_proj: auto split (4 / 5 / 5)
+    (1, 1024, 512, 0), (3, 1024, 512, 1), (16, 512, 1024, 8),             # tiny geometry, explicit split counts
+    (17, 200, 520, 3), (32, 384, 4096, 7), (40, 136, 1096, 2), (64, 1280, 640, 0),   # ragged N / K tails, 32- and 64-column accumulators
+])
+def test_gemm_tokens_bias_and_residual(abi, t, n, k, splits):
+    g = torch.Generator().manual_seed(t + n + k)
+    x = (torch.randn(t, k, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    bias = (torch.randn(n, generator=g) * 0.2).to(torch.bfloat16)
+    res = torch.randn(t, n, generator=g).to(torch.bfloat16)
+    lin = (x.float() @ w.float().t() + bias.float()).to(torch.bfloat16)
+    xd, wd = x.to(DEV), w.to(DEV)
+    out = torch.full((t, n), 7.0, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(xd, wd, out, bias=bias.to(DEV), splits=splits)
+    torch.testing.assert_close(out.cpu().float(), lin.float(), rtol=1.6e-2, atol=1e-2)
+    nob = torch.empty_like(out)
+    abi.gemm_tokens(xd, wd, nob, splits=splits)
+    torch.testing.assert_close(nob.cpu().float(), (x.float() @ w.float().t()).to(torch.bfloat16).float(), rtol=1.6e-2, atol=1e-2)
+    abi.gemm_tokens(xd, wd, out, bias=bias.to(DEV), residual=res.to(DEV), epilogue=abi.EPI_RESIDUAL, splits=splits)
+    want = (lin.float() + res.float()).to(torch.bfloat16)
+    torch.testing.assert_close(out.cpu().float(), want.float(), rtol=1.6e-2, atol=1.6e-2)
+    # in place on the residual stream, and deterministic (the split-K partial tiles are summed in rank order)
+    r2 = res.to(DEV).clone()
+    abi.gemm_tokens(xd, wd, r2, bias=bias.to(DEV), residual=r2, epilogue=abi.EPI_RESIDUAL, splits=splits)
+    assert torch.equal(bits(r2.cpu()), bits(out.cpu()))
+
+
+def test_gemm_tokens_split_counts_agree(abi):
+    """Every split count gives the same result up to the fp32 summation order (<= 1 bf16 ulp), a row of tokens equals the GEMV."""
+    g = torch.Generator().manual_seed(5)
+    t, n, k = 8, 3584, 3584
+    x = (torch.randn(t, k, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16).to(DEV)
+    outs = []
+    for s in range(1, 9):
+        o = torch.empty(t, n, dtype=torch.bfloat16, device=DEV)
+        abi.gemm_tokens(x, w, o, splits=s)
+        outs.append(o.cpu().float())
+    for o in outs[1:]:
+        torch.testing.assert_close(o, outs[0], rtol=8e-3, atol=8e-3)
+    y = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    abi.gemv_bf16(w, x[3].contiguous(), y, 0)
+    torch.testing.assert_close(y.cpu().float(), outs[0][3], rtol=8e-3, atol=8e-3)
+
+
+@pytest.mark.parametrize("t,width,k,splits", [(8, 18944, 3584, 0), (5, 1024, 512, 0), (16, 100, 200, 2), (33, 640, 320, 1)])
+def test_gemm_tokens_swiglu(abi, t, width, k, splits):
+    """SwiGLU epilogue on W = [gate rows ; up rows] (the engine's own layout): a tile pairs 64 gate rows with the 64 up rows of the same
+    columns; == silu(bf16(x Wg^T)) * bf16(x Wu^T) with the reference's roundings."""
+    g = torch.Generator().manual_seed(width + t)
+    x = (torch.randn(t, k, generator=g) * 0.5).to(torch.bfloat16)
+    wg = (torch.randn(width, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    wu = (torch.randn(width, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    gate = (x.float() @ wg.float().t()).to(torch.bfloat16)
+    up = (x.float() @ wu.float().t()).to(torch.bfloat16)
+    want = (torch.nn.functional.silu(gate.float()).to(torch.bfloat16).float() * up.float()).to(torch.bfloat16)
+    out = torch.full((t, width), 7.0, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(x.to(DEV), torch.cat([wg, wu]).to(DEV), out, epilogue=abi.EPI_SWIGLU, splits=splits)
+    torch.testing.assert_close(out.cpu().float(), want.float(), rtol=2e-2, atol=1e-2)
+
+
+def test_gemm_tokens_lm_head_rows(abi):
+    """lm_head width (1188 row tiles, two CTAs per SM, four waves): argmax over the bf16 logits == the fp32 reference's."""
+    g = torch.Generator().manual_seed(9)
+    t, n, k = 8, 152064, 3584
+    x = torch.randn(t, k, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.02).to(torch.bfloat16).to(DEV)
+    out = torch.empty(t, n, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(x, w, out)
+    ref = (x.float() @ w.float().t()).to(torch.bfloat16)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1.6e-2, atol=1e-2)
+
+
+def test_gemm_tokens_rejects_bad_arguments(abi):
+    x = torch.zeros(65, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(128, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="tokens"):
+        abi.gemm_tokens(x, w, torch.zeros(65, 128, dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(RuntimeError, match="residual"):
+        abi.gemm_tokens(x[:4].contiguous(), w, torch.zeros(4, 128, dtype=torch.bfloat16, device=DEV), epilogue=abi.EPI_RESIDUAL)
+
+
+@pytest.mark.parametrize("t,n,k,epi,splits", [(8, 4608, 3584, 0, 0), (8, 37888, 3584, 3, 0), (5, 1024, 512, 0, 2), (16, 2048, 520, 3, 1),
+                                              (1, 152064, 3584, 0, 0), (33, 256, 1096, 0, 3)])
+def test_gemm_tokens_fused_rmsnorm_equals_norm_kernel_then_gemm(abi, t, n, k, epi, splits):
+    """RMSNorm fused into the GEMM (row statistics on the epilogue warps, X panels normalised in shared memory) is BIT-identical to
+    svlm_add_rmsnorm followed by the plain GEMM: same summation order of the statistics, same rounding points."""
+    g = torch.Generator().manual_seed(t * n + k)
+    x = (torch.randn(t, k, generator=g) * 2.0).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.1 * torch.randn(k, generator=g)).to(torch.bfloat16).to(DEV)
+    h = torch.empty_like(x)
+    abi.add_rmsnorm(x, None, nw, None, h, 1e-6)
+    ref_h = o_vit.rmsnorm(x.cpu(), nw.cpu(), 1e-6)
+    torch.testing.assert_close(h.cpu().float(), ref_h.float(), rtol=8e-3, atol=8e-3)
+    cols = n // 2 if epi == abi.EPI_SWIGLU else n
+    want = torch.empty(t, cols, dtype=torch.bfloat16, device=DEV)
+    got = torch.full((t, cols), 3.0, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(h, w, want, epilogue=epi, splits=splits)
+    abi.gemm_tokens(x, w, got, epilogue=epi, splits=splits, norm_weight=nw, eps=1e-6)
+    assert torch.equal(bits(got.cpu()), bits(want.cpu()))
+
+
+@pytest.mark.parametrize("n_streams,hq,hkv,hidden", [(8, 28, 4, 3584), (3, 4, 2, 512), (1, 4, 2, 512)])
+def test_gemm_tokens_qkv_append_equals_unfused_chain(abi, tables, n_streams, hq, hkv, hidden):
+    """RMSNorm + q/k/v projection + bias + mRoPE + append into each stream's arena in ONE launch == svlm_add_rmsnorm + GEMM +
+    svlm_qkv_rope_append_streams, bit for bit (q_rot and every arena, including the rows nobody touches)."""
+    L, cap = 2, 256
+    g = torch.Generator().manual_seed(hidden + n_streams)
+    n = (hq + 2 * hkv) * 128
+    w = (torch.randn(n, hidden, generator=g) * hidden ** -0.5).to(torch.bfloat16).to(DEV)
+    b = (torch.randn(n, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(torch.bfloat16).to(DEV)
+    x = torch.randn(n_streams, hidden, generator=g).to(torch.bfloat16).to(DEV)
+    cos, sin = (t.to(DEV) for t in tables)
+    rows = torch.tensor([5 + 17 * s for s in range(n_streams)], dtype=torch.int32, device=DEV)
+    poss = torch.tensor([900 + 101 * s for s in range(n_streams)], dtype=torch.int32, device=DEV)
+
+    class C:        # what make_slots reads of a cache
+        pass
+
+    def fresh():
+        caches, arenas = [], []
+        for s in range(n_streams):
+            _, a, v = make_arena(abi, L, hkv, cap, seed=40 + s)
+            c = C(); c.arena, c.cur, c.view = a, s % 2, v
+            caches.append(c); arenas.append(a)
+        slots = abi.make_slots(caches, list(rows.split(1)), list(poss.split(1)), list(rows.split(1)))
+        return caches, arenas, slots
+
+    c1, a1, s1 = fresh()
+    c2, a2, s2 = fresh()
+    h = torch.empty_like(x)
+    abi.add_rmsnorm(x, None, nw, None, h, 1e-6)
+    qkv = torch.empty(n_streams, n, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(h, w, qkv, bias=b)
+    q_ref = torch.zeros(n_streams, hq, 128, dtype=torch.bfloat16, device=DEV)
+    abi.qkv_rope_append_streams(c1[0].view, s1, 1, qkv[:, :hq * 128], qkv[:, hq * 128:(hq + hkv) * 128], qkv[:, (hq + hkv) * 128:], hq, q_ref,
+                                cos, sin, SECTION)
+    q_got = torch.zeros_like(q_ref)
+    abi.gemm_tokens_qkv_append(c2[0].view, s2, 1, x, w, b, nw, 1e-6, hq, q_got, cos, sin)
+    torch.cuda.synchronize()
+    assert torch.equal(bits(q_got.cpu()), bits(q_ref.cpu()))
+    for s in range(n_streams):
+        assert torch.equal(bits(a2[s].cpu()), bits(a1[s].cpu())), f"arena of stream {s} differs"
+    # and the unfused chain itself against the fp32 definition of the rotation for one stream
+    assert not torch.equal(bits(a1[0][c1[0].cur, 1, 1, :, 5].cpu()), bits(a1[0][c1[0].cur, 0, 1, :, 5].cpu()))
+
+
+@pytest.mark.parametrize("t,hidden,mlp", [(8, 3584, 18944), (3, 512, 1024)])
+def test_gemm_tokens_statistics_hand_off(abi, t, hidden, mlp):
+    """A residual-epilogue launch leaves the per-tile sums of squares of the rows it wrote; the next launch's fused RMSNorm takes its
+    row statistics from them (one short read instead of a pass over X per CTA).  The table equals the fp32 definition; the consumer
+    equals svlm_add_rmsnorm + GEMM up to the summation order of the statistic (<= 1 bf16 ulp of a few outputs)."""
+    g = torch.Generator().manual_seed(hidden + t)
+    a = (torch.randn(t, mlp, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    wd = (torch.randn(hidden, mlp, generator=g) * mlp ** -0.5).to(torch.bfloat16).to(DEV)
+    x = (torch.randn(t, hidden, generator=g) * 3.0).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(torch.bfloat16).to(DEV)
+    wgu = (torch.randn(2 * mlp, hidden, generator=g) * hidden ** -0.5).to(torch.bfloat16).to(DEV)
+    tiles = -(-hidden // 128)
+    stats = torch.full((tiles, t), -1.0, dtype=torch.float32, device=DEV)
+    abi.gemm_tokens(a, wd, x, residual=x, epilogue=abi.EPI_RESIDUAL, stats_out=stats)
+    want_stats = x.float().pow(2).view(t, tiles, 128).sum(-1).t()
+    torch.testing.assert_close(stats, want_stats, rtol=1e-5, atol=1e-6)
+    h = torch.empty_like(x)
+    abi.add_rmsnorm(x, None, nw, None, h, 1e-6)
+    want = torch.empty(t, mlp, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(h, wgu, want, epilogue=abi.EPI_SWIGLU)
+    got = torch.empty_like(want)
+    abi.gemm_tokens(x, wgu, got, epilogue=abi.EPI_SWIGLU, norm_weight=nw, eps=1e-6, stats_in=stats)
+    torch.testing.assert_close(got.float(), want.float(), rtol=1.6e-2, atol=1e-2)
+    frac = (bits(got.cpu()) != bits(want.cpu())).float().mean().item()
+    assert frac < 0.02, f"{frac:.4f} of the outputs differ from the unfused chain"
