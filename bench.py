@@ -389,6 +389,47 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     byt = sum(c.seq_len for c in caches) * 2 * g.num_kv_heads * g.head_dim * 2
     out["attn_decode_streams"] = {"bound": "hbm", "achieved": byt / ta / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byt / ta / 1e9 / pk["hbm_gbs"],
                                   "us_per_launch": ta * 1e6, "splits": splits, "alg_bytes_per_launch": byt}
+    # the projections of the batched decode step: svlm_gemm_tokens, one launch each, 28 distinct weight sets per replay (>> L2)
+    e0 = multi.engines[0]
+    B = n_streams
+    xs = torch.randn(B, g.hidden, device=dev).to(torch.bfloat16)
+    xr = torch.randn(B, g.hidden, device=dev).to(torch.bfloat16)
+    att = torch.randn(B, g.num_heads * g.head_dim, device=dev).to(torch.bfloat16)
+    actb = torch.randn(B, g.mlp, device=dev).to(torch.bfloat16)
+    stat = torch.rand(-(-g.hidden // 128), B, device=dev) * 128
+    qrot = torch.empty(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
+    c0 = caches[0]
+    gt = {}
+    for name, fn, nbytes in [
+        ("gemm_tokens_norm_qkv_rope_append", lambda li, Lw: _abi.gemm_tokens_qkv_append(c0.view, slots, li, xs, Lw["wqkv"], Lw["bqkv"], Lw["ln1"], g.rms_eps,
+                                                                                      g.num_heads, qrot, c0.cos_table, c0.sin_table, stats_in=stat),
+         e0.layers[0]["wqkv"].numel() * 2),
+        ("gemm_tokens_o_residual", lambda li, Lw: _abi.gemm_tokens(att, Lw["wo"], xr, residual=xr, epilogue=_abi.EPI_RESIDUAL, stats_out=stat),
+         e0.layers[0]["wo"].numel() * 2),
+        ("gemm_tokens_norm_gate_up_swiglu", lambda li, Lw: _abi.gemm_tokens(xs, Lw["wgu"], actb, epilogue=_abi.EPI_SWIGLU, norm_weight=Lw["ln2"],
+                                                                            eps=g.rms_eps, stats_in=stat), e0.layers[0]["wgu"].numel() * 2),
+        ("gemm_tokens_down_residual", lambda li, Lw: _abi.gemm_tokens(actb, Lw["wd"], xr, residual=xr, epilogue=_abi.EPI_RESIDUAL, stats_out=stat),
+         e0.layers[0]["wd"].numel() * 2),
+    ]:
+        def run(fn=fn):
+            for li, Lw in enumerate(e0.layers):
+                fn(li, Lw)
+        run()
+        torch.cuda.synchronize()
+        grk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(grk):
+            run()
+        grk.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); grk.replay(); a1.record(); torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1) * 1e-3 / L)
+        tk = statistics.median(ts)
+        gt[name] = {"bound": "hbm", "achieved": nbytes / tk / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / tk / 1e9 / pk["hbm_gbs"],
+                    "us_per_launch": tk * 1e6, "tokens": B, "weight_bytes": nbytes}
+    out["decode_projections"] = gt
     # the chunk-prefill attention of all streams the way the batched prefill runs it: one un-split launch per stream, the streams'
     # launches side by side on their own CUDA streams (fork / join inside the graph), Tq = 300 new tokens each
     tq = 300

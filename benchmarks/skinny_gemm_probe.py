@@ -25,7 +25,7 @@ for name, n, k, epi in [("qkv", 4608, 3584, _abi.EPI_NONE), ("o", 3584, 3584, _a
         bias = torch.randn(n, device=dev).to(torch.bfloat16) if name == "qkv" else None
         tb = timed(lambda: [F.linear(x, w) for w in ws]) / copies
         row = {"shape": name, "T": m, "cublas_us": round(tb * 1e6, 2), "cublas_frac_hbm": round(byt / tb / PEAK, 3)}
-        for s in ([0] if n > 8000 else [0]):
+        for s in ([0] if n > 8000 else [0, 3, 4, 5, 6, 7, 8]):
             to = timed(lambda: [_abi.gemm_tokens(x, w, y, bias=bias, residual=res, epilogue=epi, splits=s) for w in ws]) / copies
             row[f"own_s{s}_us"] = round(to * 1e6, 2)
             if s == 0:

@@ -52,6 +52,14 @@ class MultiStreamEngine:
             e.tok_dev, e.cache.next_pos = self.tok[b:b + 1], self.next_pos[b:b + 1]
         self._tok_pinned = torch.zeros(B, dtype=torch.int64).pin_memory()
         self._active_pinned = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self._tok_ring = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._tok_events = [torch.cuda.Event() for _ in range(2)]
+        self._undo = torch.zeros(B, dtype=torch.int32, device=dev)
+        # pinned staging buffers of the look-ahead loop's mask uploads, used round-robin: a buffer is rewritten two iterations later
+        # at the earliest, after the host has waited for an event recorded behind its copy
+        self._mask_ring = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self._mask_next = 0
+        self.lookahead = os.environ.get("SVLM_MULTI_LOOKAHEAD", "1") != "0"
         g = geo
         self._q_rot = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._o = torch.zeros(B, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
@@ -285,6 +293,105 @@ class MultiStreamEngine:
             e.kv_len_dev.fill_(e.cache.seq_len)
             e.kv_after_dev.fill_(e.cache.seq_len + 1)
 
+    # ------------------------------------------------------------------ decode loops
+    def _decode_loop_plain(self, ids_all, seqs, done, argmaxes, forced):
+        """One batched decode step per token, the host reads every token before the next step (teacher forcing needs that)."""
+        B, engines = self.n, self.engines
+        n_fwd = 1
+        while True:
+            self._tok_pinned.copy_(self.tok, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            changed = False
+            for b in range(B):
+                if done[b]:
+                    continue
+                tok = int(self._tok_pinned[b])
+                argmaxes[b].append(tok)
+                f = None if forced is None else forced[b]
+                if f is not None and len(argmaxes[b]) <= len(f) and f[len(argmaxes[b]) - 1] != tok:
+                    tok = int(f[len(argmaxes[b]) - 1])
+                    engines[b].tok_dev.fill_(tok)
+                seqs[b].append(tok)
+                if tok == IM_END or len(seqs[b]) - len(ids_all[b]) >= engines[b].max_new_tokens:
+                    done[b] = changed = True
+            if all(done):
+                break
+            if changed:
+                for b in range(B):
+                    self._active_pinned[b] = 0 if done[b] else 1
+                self.active.copy_(self._active_pinned, non_blocking=True)
+            self.decode_step(done)
+            n_fwd += 1
+            for b, e in enumerate(engines):
+                if not done[b]:
+                    e.cache.seq_len += 1
+                    e.cache._seen_tokens += 1
+        return n_fwd
+
+    def _upload_mask(self, dst, values):
+        buf = self._mask_ring[self._mask_next]
+        self._mask_next = (self._mask_next + 1) % len(self._mask_ring)
+        for b, v in enumerate(values):
+            buf[b] = 1 if v else 0
+        dst.copy_(buf, non_blocking=True)
+
+    def _decode_loop_lookahead(self, ids_all, seqs, done, argmaxes):
+        """The same loop with one step of look-ahead (as in StreamingEngine.generate): the next batched step is enqueued BEFORE the
+        host has seen the current tokens, so the GPU never idles on the device->host round trip and the host-side bookkeeping.  A
+        stream whose token fills its budget is switched off ahead of the speculated step; a stream whose token turns out to be
+        <|im_end|> is rolled back afterwards (its speculated K/V row lies beyond the live length, only the counters moved)."""
+        B, engines = self.n, self.engines
+        n_fwd = 1
+        ring = self._tok_ring
+        step = 0
+        while True:
+            slot = step & 1
+            ring[slot].copy_(self.tok, non_blocking=True)
+            self._tok_events[slot].record()
+            # streams for which the token being read is the last one of their budget do not take part in the next step
+            last = [(not done[b]) and len(seqs[b]) + 1 - len(ids_all[b]) >= engines[b].max_new_tokens for b in range(B)]
+            spec = [not done[b] and not last[b] for b in range(B)]
+            speculated = any(spec) and all(engines[b].cache.seq_len + 1 <= engines[b].cache.capacity for b in range(B) if spec[b])
+            if speculated:
+                if any(last):
+                    self._upload_mask(self.active, spec)
+                self.decode_step([not x for x in spec])
+            self._tok_events[slot].synchronize()
+            ended = []
+            for b in range(B):
+                if done[b]:
+                    continue
+                tok = int(ring[slot][b])
+                argmaxes[b].append(tok)
+                seqs[b].append(tok)
+                if tok == IM_END or last[b]:
+                    done[b] = True
+                    if speculated and spec[b]:
+                        ended.append(b)
+                elif speculated:
+                    engines[b].cache.seq_len += 1
+                    engines[b].cache._seen_tokens += 1
+            if speculated:
+                n_fwd += 1
+            if ended:                                       # undo the speculated step of the streams that had just ended
+                self._upload_mask(self._undo, [b in ended for b in range(B)])
+                self.kv_len.sub_(self._undo)
+                self.next_pos.sub_(self._undo)
+                self.kv_after.copy_(self.kv_len + 1)
+                self._upload_mask(self.active, [not d for d in done])
+            if all(done):
+                break
+            if not speculated:
+                self._upload_mask(self.active, [not d for d in done])
+                self.decode_step(done)                      # raises the capacity error
+                n_fwd += 1
+                for b, e in enumerate(engines):
+                    if not done[b]:
+                        e.cache.seq_len += 1
+                        e.cache._seen_tokens += 1
+            step += 1
+        return n_fwd
+
     # ------------------------------------------------------------------ one chunk of every stream
     def step(self, prompts, pixels, grid, previous_text="", forced=None, sync_timing=True):
         """One chunk for each stream (`prompts[b]`, `pixels[b]`; same grid).  `forced[b]`: teacher-forced tokens of stream b
@@ -330,34 +437,10 @@ class MultiStreamEngine:
         argmaxes = [[] for _ in range(B)]
         self.active.fill_(1)
         n_fwd = 1
-        while True:
-            self._tok_pinned.copy_(self.tok, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            changed = False
-            for b in range(B):
-                if done[b]:
-                    continue
-                tok = int(self._tok_pinned[b])
-                argmaxes[b].append(tok)
-                f = None if forced is None else forced[b]
-                if f is not None and len(argmaxes[b]) <= len(f) and f[len(argmaxes[b]) - 1] != tok:
-                    tok = int(f[len(argmaxes[b]) - 1])
-                    engines[b].tok_dev.fill_(tok)
-                seqs[b].append(tok)
-                if tok == IM_END or len(seqs[b]) - len(ids_all[b]) >= engines[b].max_new_tokens:
-                    done[b] = changed = True
-            if all(done):
-                break
-            if changed:
-                for b in range(B):
-                    self._active_pinned[b] = 0 if done[b] else 1
-                self.active.copy_(self._active_pinned, non_blocking=True)
-            self.decode_step(done)
-            n_fwd += 1
-            for b, e in enumerate(engines):
-                if not done[b]:
-                    e.cache.seq_len += 1
-                    e.cache._seen_tokens += 1
+        if forced is None and self.use_graph and self.lookahead:
+            n_fwd = self._decode_loop_lookahead(ids_all, seqs, done, argmaxes)
+        else:
+            n_fwd = self._decode_loop_plain(ids_all, seqs, done, argmaxes, forced)
         if sync_timing:
             torch.cuda.synchronize()
         t_gen = time.perf_counter() - t0

@@ -71,3 +71,41 @@ def test_two_streams_eager_equals_graph():
     for ea, eb in zip(a.engines, b.engines):
         assert ea.prev_ids.tolist() == eb.prev_ids.tolist()
         assert ea.cache.seq_len == eb.cache.seq_len
+
+
+def test_multistream_lookahead_loop_equals_plain_loop():
+    """The batched decode loop with one step of look-ahead (next step enqueued before the host has read the current tokens; streams
+    whose turn ends are switched off ahead of it or rolled back after it) == the plain read-then-step loop: same ids per stream, same
+    cache lengths, device-side counters and arenas bit for bit.  Four-id vocabulary incl. <|im_end|>: turns end early all the time,
+    at different steps in different streams."""
+    from streaming_vlm_b200.engine import IM_END
+    from streaming_vlm_b200.multi_stream import MultiStreamEngine
+    geo = TINY
+    w_cpu = synthetic.random_weights(geo, seed=0)
+    suppress = torch.ones(geo.vocab, dtype=torch.bool)
+    suppress[torch.tensor([IM_END, 1000, 1001, 1002])] = False
+    multis = []
+    for look in (True, False):
+        m = MultiStreamEngine({k: v.clone() for k, v in w_cpu.items()}, geo, 3, capacity=4096, window_size=4, text_round=4, text_sink=16,
+                              text_sliding_window=24, suppress=suppress, prefill_bucket=1)
+        m.lookahead = look
+        multis.append(m)
+    early = 0
+    for i in range(12):
+        prompts, pixels = [], []
+        for b in range(3):
+            px, grid = synthetic.patchify(synthetic.frames(1000 * b + i, 112, 112), geo)
+            prompts.append(synthetic.round_prompt(i, 16, 4 + 3 * b))
+            pixels.append(px.to("cuda"))
+        ra, rb = (m.step(prompts, pixels, grid) for m in multis)
+        for b in range(3):
+            assert ra[b]["ids"] == rb[b]["ids"], f"chunk {i} stream {b}"
+            assert ra[b]["cache_len"] == rb[b]["cache_len"] and ra[b]["runs"] == rb[b]["runs"], f"chunk {i} stream {b}"
+            early += len(ra[b]["new_tokens"]) < multis[0].engines[b].max_new_tokens
+        for name in ("kv_len", "next_pos"):
+            assert torch.equal(getattr(multis[0], name), getattr(multis[1], name)), f"chunk {i}: {name}"
+    assert early >= 5, "the test streams never ended a turn early"
+    for b in range(3):
+        ca, cb = multis[0].engines[b].cache, multis[1].engines[b].cache
+        n = ca.seq_len
+        assert torch.equal(ca.arena[ca.cur, :, :, :, :n].view(torch.int16), cb.arena[cb.cur, :, :, :, :n].view(torch.int16)), f"stream {b}: arenas"
