@@ -429,7 +429,14 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
         tk = statistics.median(ts)
         gt[name] = {"bound": "hbm", "achieved": nbytes / tk / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / tk / 1e9 / pk["hbm_gbs"],
                     "us_per_launch": tk * 1e6, "tokens": B, "weight_bytes": nbytes}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        traffic = {}
+    for k_, v_ in gt.items():
+        v_["traffic"] = traffic.get(k_)
     out["decode_projections"] = gt
+    out["attn_decode_streams"]["traffic"] = traffic.get("attn_decode_streams")
     # the chunk-prefill attention of all streams the way the batched prefill runs it: one un-split launch per stream, the streams'
     # launches side by side on their own CUDA streams (fork / join inside the graph), Tq = 300 new tokens each
     tq = 300

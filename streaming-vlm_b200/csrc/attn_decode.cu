@@ -74,6 +74,11 @@ __device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_shared_cluster_f32_(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -137,6 +142,9 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
     const int n_tiles = max(min(n_total, my_begin + tps) - my_begin, 0);
     const int kv_coord = p.kv_head_base + head;
 
+    float c_o[G], c_m[G], c_l[G];      // softmax warps: this split's (O^T lane, m, l) per head, handed to the cluster merge below
+#pragma unroll
+    for (int h = 0; h < G; ++h) { c_o[h] = 0.f; c_m[h] = -INFINITY; c_l[h] = 0.f; }
     constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 16, 0, 0);   // A = K tile (K-major), B = Q (K-major)
     constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 16, 1, 0);   // A = V tile read MN-major, B = P^T (K-major)
 
@@ -335,33 +343,51 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
                     if (row == h) p.part_ml[(int64_t)split * p.rows_total + strm * p.Hq + head * G + h] = make_float2(m_run[h], l_tot[h]);
             }
         } else {
-            // publish this split's (m, l, O^T) in shared memory for the cluster merge below; the P^T operand buffers are free
-            // (the last PV UMMA has completed) and hold G x 128 floats
-            float* xo = reinterpret_cast<float*>(sP);
 #pragma unroll
-            for (int h = 0; h < G; ++h) xo[h * 128 + d] = __uint_as_float(orow[h]);
-#pragma unroll
-            for (int h = 0; h < G; ++h)
-                if (row == h) { sh->wmax[0][0][h] = m_run[h]; sh->wmax[1][0][h] = l_tot[h]; }
+            for (int h = 0; h < G; ++h) { c_o[h] = __uint_as_float(orow[h]); c_m[h] = m_run[h]; c_l[h] = l_tot[h]; }
         }
     }
 
     if (p.cluster > 1) {
-        // ---- split merge inside the cluster: rank 0 reads every peer's (m, l, O^T) over distributed shared memory, so the partial
-        // sums of `cluster` splits never travel through HBM / L2 and (when cluster == num_splits) no merge kernel is launched
-        cluster_sync_all();
-        if (cluster_ctarank() == 0 && warp >= 2) {
+        // ---- split merge inside the cluster, PUSH based: once every CTA's K/V ring is dead (barrier 1), the peers store their
+        // (m, l, O^T) into the leader's ring (st.shared::cluster, fire and forget), barrier 2, and the leader merges out of its own
+        // shared memory.  The partial sums never travel through HBM / L2 and, when cluster == num_splits, no merge kernel is launched.
+        // (Round 2 first had the leader PULL its peers' results over DSMEM: one remote-load round trip per peer in sequence, 13.0 us
+        // instead of 9.8 us with the merge kernel for a single stream.)
+        constexpr int LAND = G * 128 + 16;                       // floats per rank: O^T [G][128], m [8], l [8]
+        float* land = reinterpret_cast<float*>(sKV);
+        const uint32_t rank = cluster_ctarank();
+        cluster_arrive_release_();
+        cluster_wait_acquire_();
+        if (warp >= 2) {
             const int d = (warp & 3) * 32 + lane;
-            const uint32_t xo_local = smem_u32(sP), m_local = smem_u32(&sh->wmax[0][0][0]), l_local = smem_u32(&sh->wmax[1][0][0]);
+            if (rank == 0) {
+#pragma unroll
+                for (int h = 0; h < G; ++h) land[h * 128 + d] = c_o[h];
+#pragma unroll
+                for (int h = 0; h < G; ++h)
+                    if (d == h) { land[G * 128 + h] = c_m[h]; land[G * 128 + 8 + h] = c_l[h]; }
+            } else {
+                const uint32_t base = mapa_shared(smem_u32(land + rank * LAND), 0);
+#pragma unroll
+                for (int h = 0; h < G; ++h) st_shared_cluster_f32_(base + (h * 128 + d) * 4, c_o[h]);
+#pragma unroll
+                for (int h = 0; h < G; ++h)
+                    if (d == h) { st_shared_cluster_f32_(base + (G * 128 + h) * 4, c_m[h]); st_shared_cluster_f32_(base + (G * 128 + 8 + h) * 4, c_l[h]); }
+            }
+        }
+        cluster_arrive_release_();
+        cluster_wait_acquire_();
+        if (rank == 0 && warp >= 2) {
+            const int d = (warp & 3) * 32 + lane;
             float M[G], L[G], O[G];
 #pragma unroll
             for (int h = 0; h < G; ++h) { M[h] = -INFINITY; L[h] = 0.f; O[h] = 0.f; }
             for (int r = 0; r < p.cluster; ++r) {
-                const uint32_t xo_r = mapa_shared(xo_local, r), m_r = mapa_shared(m_local, r), l_r = mapa_shared(l_local, r);
+                const float* lr = land + r * LAND;
 #pragma unroll
                 for (int h = 0; h < G; ++h) {
-                    const float m = ld_shared_cluster_f32(m_r + h * 4), l = ld_shared_cluster_f32(l_r + h * 4);
-                    const float o = ld_shared_cluster_f32(xo_r + (h * 128 + d) * 4);
+                    const float m = lr[G * 128 + h], l = lr[G * 128 + 8 + h], o = lr[h * 128 + d];
                     const float m_new = fmaxf(M[h], m);
                     const float a = (M[h] == -INFINITY) ? 0.f : ex2_approx(M[h] - m_new);
                     const float b = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new);
@@ -385,7 +411,6 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
                 }
             }
         }
-        cluster_sync_all();                                       // peers keep their shared memory alive until rank 0 has read it
     }
 
     tc_fence_before();
@@ -400,6 +425,11 @@ static int launch_decode_s(const DecMaps& maps, const DecParams& p, dim3 grid, c
         cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<G, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem(SLOTS));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attn_decode_kernel, %d B smem) failed: %s", dec_smem(SLOTS), cudaGetErrorString(e));
+            return SVLM_ECUDA;
+        }
+        e = cudaFuncSetAttribute(attn_decode_kernel<G, SLOTS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attn_decode_kernel, non-portable cluster size) failed: %s", cudaGetErrorString(e));
             return SVLM_ECUDA;
         }
         attr_done = true;
@@ -482,22 +512,22 @@ static int decode_launch_common(const svlm_arena_t* geom, const void* const* are
     }
     p.Hq = q_heads; p.G = G; p.D = D;
     p.kv_len = kv_len; p.num_splits = num_splits;
-    // Splits of one (stream, kv head) that sit in one thread-block cluster merge through distributed shared memory.  Measured on B200
-    // (profiles/r2g_decode_cluster_merge_ab.md): with the few splits of the multi-stream launch (4 per stream and head) the merge
-    // kernel and the fp32 round trip of the partials disappear (22.2 -> 21.2 us for 8 streams x 5.8k keys); clusters of 8 for the
-    // 23-37 splits of a single stream are SLOWER than the separate merge launch (9.8 -> 13.0 us at 5.8k, 27.8 -> 48.2 us at 64k:
-    // rank 0 walks its peers' results serially while they hold their SMs), so that path keeps the merge kernel.
-    // SVLM_DECODE_CLUSTER = 1 / 2 / 4 / 8 overrides the largest cluster size for both.
+    // Splits of one (stream, kv head) that sit in one thread-block cluster merge through distributed shared memory (push based, see the
+    // kernel): no merge launch, no fp32 round trip of the partials.  Measured on B200 (benchmarks/decode_attn_cluster_sweep.py,
+    // profiles/r2k_decode_cluster_push_sweep.jsonl): for the few splits of the multi-stream launch (4 per stream and head) it wins;
+    // for ONE stream at 5.8k keys 8-CTA clusters take 10.9 us (merge kernel with 8 splits: 11.8 us) and 16-CTA clusters 10.9 us
+    // (merge kernel: 10.1 us), but 23 splits + the merge kernel, which overlaps the attention's tail through programmatic dependent
+    // launch, remain the fastest (9.6 us) -- the single-stream launch is bound by its fixed costs, not by the merge.
+    // SVLM_DECODE_CLUSTER = 1 / 2 / 4 / 8 / 16 overrides the largest cluster size (16 = "non-portable", opted in per kernel).
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("SVLM_DECODE_CLUSTER");
         forced = e ? atoi(e) : 0;
-        if (forced != 1 && forced != 2 && forced != 4 && forced != 8) forced = 0;
+        if (forced != 1 && forced != 2 && forced != 4 && forced != 8 && forced != 16) forced = 0;
     }
-    const int max_cluster = forced ? forced : (n_streams > 1 && num_splits <= 4 ? 4 : 1);
+    const int max_cluster = forced ? forced : (n_streams > 1 ? 8 : 1);
     p.cluster = 1;
-    for (int c = max_cluster; c > 1; c >>= 1)
-        if (num_splits % c == 0) { p.cluster = c; break; }
+    if (num_splits <= max_cluster && (num_splits & (num_splits - 1)) == 0) p.cluster = num_splits;
     const int n_parts = num_splits / p.cluster;
     p.rows_total = n_streams * q_heads;
     p.kv_head_base = layer * H;
