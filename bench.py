@@ -25,6 +25,7 @@ imported here) on the host cores: full-depth steady-state chunks (28 
 nothing extrapolated (SVLM_CPU_SAMPLE=scaled restores the layer-count-scaled sample for small hosts).
 """
 import argparse
+import gc
 import copy
 import json
 import math
@@ -436,7 +437,7 @@ def multi_stream_leg(engine, n_streams, rounds, warmup, rank, dev, pk):
     for k_, v_ in gt.items():
         v_["traffic"] = traffic.get(k_)
     out["decode_projections"] = gt
-    out["attn_decode_streams"]["traffic"] = traffic.get("attn_decode_streams")
+    out["attn_decode_streams"]["traffic"] = traffic.get("attn_decode_streams") if n_streams == 8 else None
     # the chunk-prefill attention of all streams the way the batched prefill runs it: one un-split launch per stream, the streams'
     # launches side by side on their own CUDA streams (fork / join inside the graph), Tq = 300 new tokens each
     tq = 300
@@ -760,18 +761,22 @@ def run_gpu(args):
                 line["config3_sweep"] = config3_sweep(pk, dev)
             except Exception as exc:   # noqa: BLE001   (an extra leg must never cost the headline line)
                 line["config3_sweep"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    if args.streams > 1:
-        # extra leg: it must never cost the headline line (every rank still takes part in the all-reduce below)
+    for key, n_streams in (("multi_stream", args.streams), ("multi_stream_16", args.streams2)):
+        if n_streams <= 1 or (key == "multi_stream_16" and n_streams == args.streams):
+            continue
+        # extra legs: they must never cost the headline line (every rank still takes part in the all-reduce below)
         try:
-            ms = multi_stream_leg(engine, args.streams, max(2, args.steps // 2), 2, rank, dev, pk)
+            ms = multi_stream_leg(engine, n_streams, max(2, args.steps // 2), 2, rank, dev, pk)
         except Exception as exc:   # noqa: BLE001
-            ms = {"streams": args.streams, "value": 0.0, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+            ms = {"streams": n_streams, "value": 0.0, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        gc.collect()
+        torch.cuda.empty_cache()
         if dist is not None:
             tt = torch.tensor([ms["value"]], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.SUM)
             ms["value_all_gpus"] = float(tt[0])
         if rank == 0:
-            line["multi_stream"] = ms
+            line[key] = ms
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -865,6 +870,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="streams per GPU of the extra multi-stream leg (BASELINE configs[3]); 1 = skip")
+    ap.add_argument("--streams2", type=int, default=16, help="streams per GPU of the second multi-stream leg (`multi_stream_16`); 1 = skip")
     ap.add_argument("--generation", default="reference", choices=["reference", "greedy"],
                     help="token selection of the timed drop-in legs: the reference's sampling config or greedy")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[2] 4k-64k kernel sweep")

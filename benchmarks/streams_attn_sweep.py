@@ -10,7 +10,7 @@ from streaming_vlm_b200.inference.generate.streaming_cache import StreamingCache
 
 dev = torch.device("cuda")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5789
-for B in (2, 4, 8):
+for B in [int(a) for a in sys.argv[2:]] or (2, 4, 8, 16):
     caches = [StreamingCache(G, 8192, dev) for _ in range(B)]
     for c in caches:
         c.arena[0].normal_(0, 0.5)

@@ -40,7 +40,7 @@ extern "C" {
 #define SVLM_ENODEV   -3   /* no sm_100 device / driver entry point unavailable */
 
 #define SVLM_MAX_RUNS 32   /* maximum number of gather runs per compaction launch */
-#define SVLM_MAX_STREAMS 8 /* streams whose decode steps share one launch (section 8) */
+#define SVLM_MAX_STREAMS 16 /* streams whose decode steps share one launch (section 8) */
 #define SVLM_MAX_TP 8      /* ranks of one tensor-parallel group (one NVLink / NVSwitch node) */
 
 #define SVLM_PLANE_K_RAW 0

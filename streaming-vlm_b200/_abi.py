@@ -40,7 +40,7 @@ class StreamSlot(Structure):
     _fields_ = [("arena_base", c_void_p), ("buffer", c_int32), ("row_dev", c_void_p), ("pos_dev", c_void_p), ("kv_len_dev", c_void_p)]
 
 
-MAX_STREAMS = 8
+MAX_STREAMS = 16
 MAX_TP = 8
 TP_DECODE_OFFSET = 1024
 

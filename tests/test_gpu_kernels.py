@@ -467,7 +467,9 @@ def test_qkv_rope_append_streams_matches_single_stream(abi, tables):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,kv_lens,splits", [(3, [300, 5343, 129], 8), (8, [5789, 5700, 4100, 128, 1, 6000, 5789, 2500], 16),
-                                              (2, [1000, 77], 1)])
+                                              (2, [1000, 77], 1),
+                                              (16, [5789, 12, 4100, 128, 1, 6000, 5789, 2500, 300, 5343, 129, 3000, 2047, 2048, 2049, 640], 2),
+                                              (12, [700 + 411 * b for b in range(12)], 4)])
 def test_attn_decode_streams_matches_single_stream(abi, B, kv_lens, splits):
     """One launch over B streams == B single-stream launches, bit for bit (same kernel, same split boundaries per stream)."""
     Hq, H, L = 28, 4, 2
@@ -486,7 +488,12 @@ def test_attn_decode_streams_matches_single_stream(abi, B, kv_lens, splits):
     slots = abi.make_slots(caches, rows, pos, kv)
     abi.attn_decode_streams(abi.ArenaView(arenas[0][1]), slots, layer, q, out, Hq, cap, scale, splits, wsB)
     torch.cuda.synchronize()
-    assert torch.equal(bits(out.cpu()), bits(ref.cpu()))
+    if splits > 1 and splits <= 8 and splits & (splits - 1) == 0:
+        # the batched launch merges these split counts inside thread-block clusters, the single-stream launch through the merge
+        # kernel: same partial results, a different order of the fp32 merge arithmetic (<= 1 bf16 ulp of a few outputs)
+        torch.testing.assert_close(out.cpu().float(), ref.cpu().float(), rtol=8e-3, atol=2e-3)
+    else:
+        assert torch.equal(bits(out.cpu()), bits(ref.cpu()))
     # and against the definition for one of the streams
     b = 0
     cpu = arenas[b][0]
@@ -498,9 +505,10 @@ def test_attn_decode_streams_matches_single_stream(abi, B, kv_lens, splits):
 def test_streams_argument_errors(abi):
     cpu, dev, view = make_arena(abi, 1, 2, 256, seed=3)
     one = torch.zeros(1, dtype=torch.int32, device=DEV)
-    q = torch.zeros(9, 4, 128, dtype=torch.bfloat16, device=DEV)
+    too_many = abi.MAX_STREAMS + 1
+    q = torch.zeros(too_many, 4, 128, dtype=torch.bfloat16, device=DEV)
     with pytest.raises(ValueError):
-        abi.make_slots([_FakeCache(dev, 0)] * 9, [one] * 9, [one] * 9, [one] * 9)
+        abi.make_slots([_FakeCache(dev, 0)] * too_many, [one] * too_many, [one] * too_many, [one] * too_many)
     slots = abi.make_slots([_FakeCache(dev, 0)], [one], [one], [one])
     with pytest.raises(RuntimeError, match="workspace"):
         abi.attn_decode_streams(view, slots, 0, q[:1], q[:1].clone(), 4, 256, 0.1, 4, None)
@@ -840,7 +848,7 @@ def test_gemm_tokens_fused_rmsnorm_equals_norm_kernel_then_gemm(abi, t, n, k, ep
     assert torch.equal(bits(got.cpu()), bits(want.cpu()))
 
 
-@pytest.mark.parametrize("n_streams,hq,hkv,hidden", [(8, 28, 4, 3584), (3, 4, 2, 512), (1, 4, 2, 512)])
+@pytest.mark.parametrize("n_streams,hq,hkv,hidden", [(8, 28, 4, 3584), (3, 4, 2, 512), (1, 4, 2, 512), (16, 4, 2, 512), (13, 28, 4, 3584)])
 def test_gemm_tokens_qkv_append_equals_unfused_chain(abi, tables, n_streams, hq, hkv, hidden):
     """RMSNorm + q/k/v projection + bias + mRoPE + append into each stream's arena in ONE launch == svlm_add_rmsnorm + GEMM +
     svlm_qkv_rope_append_streams, bit for bit (q_rot and every arena, including the rows nobody touches)."""
@@ -852,7 +860,7 @@ def test_gemm_tokens_qkv_append_equals_unfused_chain(abi, tables, n_streams, hq,
     nw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(torch.bfloat16).to(DEV)
     x = torch.randn(n_streams, hidden, generator=g).to(torch.bfloat16).to(DEV)
     cos, sin = (t.to(DEV) for t in tables)
-    rows = torch.tensor([5 + 17 * s for s in range(n_streams)], dtype=torch.int32, device=DEV)
+    rows = torch.tensor([5 + 13 * s for s in range(n_streams)], dtype=torch.int32, device=DEV)
     poss = torch.tensor([900 + 101 * s for s in range(n_streams)], dtype=torch.int32, device=DEV)
 
     class C:        # what make_slots reads of a cache

@@ -64,6 +64,15 @@ def test_three_streams_small_windows(batch_prefill):
     assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
 
 
+def test_ten_streams_one_batched_step():
+    """More than 8 streams per launch (SVLM_MAX_STREAMS = 16): 10 streams through the batched ViT / prefill / decode, each against its
+    own oracle session."""
+    mism, total, multi = _run(10, 5, 112, 112, 4, 4, 16, 24)
+    assert len({tuple(e.prev_ids.tolist()) for e in multi.engines}) == 10
+    record("multistream_10", greedy_mismatches=mism, greedy_tokens=total)
+    assert mism <= max(1, int(total * MAX_NEAR_TIE_FRACTION)), (mism, total)
+
+
 def test_two_streams_eager_equals_graph():
     """The CUDA-graph replay of the batched step and its eager execution produce the same tokens."""
     _, _, a = _run(2, 6, 112, 112, 4, 4, 16, 24, use_graph=True)
