@@ -62,6 +62,15 @@ def make_arena(abi, L, H, cap, seed=0, fill=True):
     return a, dev, abi.ArenaView(dev)
 
 
+def aligned_clone(t):
+    """A copy of `t` whose base is 1024-byte aligned (`clone()` only promises the caching allocator's 512 bytes)."""
+    store = torch.empty(t.numel() + 512, dtype=t.dtype, device=t.device)
+    skip = (-store.data_ptr() % 1024) // t.element_size()
+    out = store[skip:skip + t.numel()].view(t.shape)
+    out.copy_(t)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("m,n,k,act,perm", [(256, 5120, 5120, 1, False), (256, 3584, 5120, 0, True), (100, 72, 200, 1, True),
                                             (128, 128, 64, 0, False), (1024, 3840, 1280, 0, False), (37, 512, 1280, 1, False)])
@@ -445,7 +454,7 @@ def test_qkv_rope_append_streams_matches_single_stream(abi, tables):
     B, L, H, cap, Hq = 3, 2, 2, 512, 4
     kv_lens, curs = [200, 37, 511], [1, 0, 1]
     arenas, caches, rows, after, pos = _stream_setup(abi, B, L, H, cap, kv_lens, curs)
-    ref = [a[1].clone() for a in arenas]
+    ref = [aligned_clone(a[1]) for a in arenas]
     g = torch.Generator().manual_seed(8)
     qkv = torch.randn(B, (Hq + 2 * H) * 128, generator=g).to(torch.bfloat16).to(DEV)
     q, k, v = qkv[:, :Hq * 128], qkv[:, Hq * 128:(Hq + H) * 128], qkv[:, (Hq + H) * 128:]
