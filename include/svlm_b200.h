@@ -324,7 +324,8 @@ int svlm_frames_resize_bicubic(const void* in_thwc_u8, int n_frames, int height,
  *   svlm_tp_gemv_allreduce : decode step.  y = residual + bf16(sum_r W_r x_r): each CTA streams its rows of W (bf16 [N][K_local])
  *       and PUSHES its fp32 partial sums to every rank's region as 8-byte (value, epoch) words (NVLink stores; the epoch travels
  *       with the value, so there is no flag, fence or round trip); the CTA that finishes last waits until the words of all ranks
- *       carry this epoch, sums the W partial vectors in rank order, adds the residual, writes y.
+ *       carry this epoch, sums the W partial vectors in rank order, adds the residual, writes y.  (SVLM_TP_PUSH=0: the partial sums
+ *       stay in the rank's own region, the last CTA meets the peers through the flag words and pulls their vectors.)
  *   svlm_tp_allreduce_rows : chunk prefill.  The partial products [rows][cols] bf16 were written into this rank's region by the
  *       GEMM (svlm_tp_ctx_t offsets below); out = residual + bf16(sum_r part_r).
  * Symmetric buffer layout (bytes, identical on every rank):  [0, 1024) flag words (uint32 per peer rank), then two regions of

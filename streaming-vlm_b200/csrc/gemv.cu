@@ -25,6 +25,7 @@ struct TpDev {
     uint32_t* peer_flags[SVLM_MAX_TP];      // rank r's flag array [SVLM_MAX_TP]; flags[q] = last epoch rank q announced to r
     uint32_t* seq;                          // local: all-reduces completed so far (the epoch counter)
     uint32_t* done;                         // local: CTAs of the current launch that have finished their part (0 between launches)
+    int push;                               // 1: partial sums are pushed to every rank as (value, epoch) words; 0: flag rendezvous + pull
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -44,6 +45,11 @@ __device__ __forceinline__ uint4 ld_relaxed_sys_u4(const void* p) {
     return v;
 }
 
+__device__ __forceinline__ float2 ld_relaxed_sys_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_sys_u2(void* p, uint32_t a, uint32_t b) {
     asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
@@ -332,14 +338,18 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
                     p.scores_out[n] = -INFINITY;
                 }
             } else if (MODE == GEMV_TP) {
-                // fp32 partial sum of this rank's K slice, PUSHED to every rank (NVLink stores, fire and forget) as an 8-byte
-                // (value, epoch) word: the epoch travels with the value, so the receiver needs no separate flag, fence or round trip
-                const uint32_t epoch = *p.tp.seq + 1u;
+                if (p.tp.push) {
+                    // fp32 partial sum of this rank's K slice, PUSHED to every rank (NVLink stores, fire and forget) as an 8-byte
+                    // (value, epoch) word: the epoch travels with the value, so the receiver needs no separate flag, fence or round trip
+                    const uint32_t epoch = *p.tp.seq + 1u;
 #pragma unroll
-                for (int r = 0; r < SVLM_MAX_TP; ++r)
-                    if (r < p.tp.world)
-                        st_relaxed_sys_u2(reinterpret_cast<uint2*>(const_cast<void*>(p.tp.peer_part[r])) + (size_t)p.tp.rank * p.N + n,
-                                          __float_as_uint(v), epoch);
+                    for (int r = 0; r < SVLM_MAX_TP; ++r)
+                        if (r < p.tp.world)
+                            st_relaxed_sys_u2(reinterpret_cast<uint2*>(const_cast<void*>(p.tp.peer_part[r])) + (size_t)p.tp.rank * p.N + n,
+                                              __float_as_uint(v), epoch);
+                } else {
+                    p.tp_part[n] = v;                                              // stays in this rank's region; the peers pull it
+                }
             } else if (MODE == GEMV_SWIGLU) {
                 const float gt = round_bf16(v), up = round_bf16(v2);
                 const float sl = round_bf16(gt / (1.0f + __expf(-gt)));
@@ -374,8 +384,10 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
         }
         __syncthreads();
         if (!is_last) return;
+        uint32_t epoch;
+        if (p.tp.push) {
         // every rank's words land in THIS rank's buffer ([source rank][N] x (value, epoch)); a word is valid once its epoch matches
-        const uint32_t epoch = *p.tp.seq + 1u;
+        epoch = *p.tp.seq + 1u;
         const uint2* mine = reinterpret_cast<const uint2*>(p.tp.peer_part[p.tp.rank]);
         const long long t0 = clock64();
         for (int n = t * 2; n < p.N; n += GEMV_THREADS * 2) {
@@ -398,6 +410,24 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvParams p) 
             }
             const uint32_t rv = *reinterpret_cast<const uint32_t*>(p.residual + n);
             *reinterpret_cast<uint32_t*>(p.y + n) = pack_bf16(round_bf16(s0) + bf16_lo(rv), round_bf16(s1) + bf16_hi(rv));
+        }
+        } else {
+        // flag rendezvous with the peers, then PULL their partial vectors (fp32 [N] in each rank's own region): the form this kernel
+        // started with, kept for A/B (SVLM_TP_PUSH=0)
+        epoch = tp_rendezvous(p.tp);
+        for (int n = t * 2; n < p.N; n += GEMV_THREADS * 2) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < SVLM_MAX_TP; ++r) {
+                if (r < p.tp.world) {
+                    const float2 w = ld_relaxed_sys_f2(reinterpret_cast<const float*>(p.tp.peer_part[r]) + n);
+                    s0 += w.x;
+                    s1 += w.y;
+                }
+            }
+            const uint32_t rv = *reinterpret_cast<const uint32_t*>(p.residual + n);
+            *reinterpret_cast<uint32_t*>(p.y + n) = pack_bf16(round_bf16(s0) + bf16_lo(rv), round_bf16(s1) + bf16_hi(rv));
+        }
         }
         __syncthreads();
         if (t == 0) { *p.tp.seq = epoch; *p.tp.done = 0u; }
@@ -672,6 +702,14 @@ static int make_tp_dev(const svlm_tp_ctx_t* ctx, int which, size_t region_offset
     }
     out->seq = ctx->seq;
     out->done = ctx->done;
+    // decode all-reduce: push (value, epoch) words (default); SVLM_TP_PUSH=0 selects the flag rendezvous + pull form (A/B on one 8-GPU
+    // box at TP = 8: 12.9 / 13.2 frames/s pushed, 10.5 / 10.7 pulled; TP = 2: 11.2 pushed, 10.7 pulled)
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("SVLM_TP_PUSH");
+        forced = e ? (e[0] == '1' ? 1 : 0) : -1;
+    }
+    out->push = forced >= 0 ? forced : 1;
     return SVLM_OK;
 }
 
