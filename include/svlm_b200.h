@@ -40,6 +40,7 @@ extern "C" {
 #define SVLM_ENODEV   -3   /* no sm_100 device / driver entry point unavailable */
 
 #define SVLM_MAX_RUNS 32   /* maximum number of gather runs per compaction launch */
+#define SVLM_ATTN_EARLY_KV 1 /* flag of svlm_attn_causal / svlm_attn_decode_streams */
 #define SVLM_MAX_STREAMS 16 /* streams whose decode steps share one launch (section 8) */
 #define SVLM_MAX_TP 8      /* ranks of one tensor-parallel group (one NVLink / NVSwitch node) */
 
@@ -125,11 +126,16 @@ int svlm_qkv_rope_append(const svlm_arena_t* arena, int buffer, int layer, const
  *                it is read from device memory (kv_len then is an upper bound used for the grid)
  *   num_splits : >= 1; with > 1 the KV range is split across CTAs and merged by a second
  *                kernel.  workspace: fp32, svlm_attn_workspace_bytes(...) bytes.
+ *   flags      : 0, or SVLM_ATTN_EARLY_KV (decode only, Tq = 1, with kv_len_dev): the caller guarantees that *kv_len_dev and
+ *                the K/V rows below kv_len - 1 were NOT written by the launch immediately before this one in the stream (the
+ *                decode chain: the preceding q/k/v launch appends row kv_len - 1 only; the counters were advanced at the end of
+ *                the previous token).  The kernel, which is launched with programmatic stream serialization, then reads the
+ *                length and requests those K/V tiles BEFORE the grid dependency resolves.
  * ------------------------------------------------------------------------------------- */
 size_t svlm_attn_workspace_bytes(int n_q_tokens, int q_heads, int head_dim, int num_splits);
 int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int n_q_tokens,
                      int q_heads, int kv_len, const int32_t* kv_len_dev, int num_splits, void* workspace,
-                     size_t workspace_bytes, float scale, void* stream);
+                     size_t workspace_bytes, float scale, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (5) ViT attention: 2-D RoPE + packed variable-length non-causal attention.
@@ -281,7 +287,7 @@ int svlm_qkv_rope_append_streams(const svlm_arena_t* geometry, const svlm_stream
                                  int table_rows, const int32_t* mrope_section_host, void* stream);
 int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
                              const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
-                             size_t workspace_bytes, float scale, void* stream);
+                             size_t workspace_bytes, float scale, int flags, void* stream);
 /* The q/k/v projection of the batched decode step with everything around it in ONE launch (replaces svlm_add_rmsnorm + GEMM + bias +
  * svlm_qkv_rope_append_streams; reference: input_layernorm + q/k/v_proj + apply_multimodal_rotary_pos_emb + cache update,
  * language_forward.py:47-66, 175-192, generate/streaming_cache.py:72-73): X [n_streams][hidden] is normalised (norm_weight, eps),

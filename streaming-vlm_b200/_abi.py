@@ -94,7 +94,7 @@ def lib() -> ctypes.CDLL:
                                        c_int, vp, vp, c_int, vp, vp, vp, c_int, i32p, vp]
     L.svlm_attn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.svlm_attn_workspace_bytes.restype = c_size_t
-    L.svlm_attn_causal.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, vp, c_size_t, c_float, vp]
+    L.svlm_attn_causal.argtypes = [POINTER(Arena), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, vp, c_size_t, c_float, c_int, vp]
     L.svlm_vit_rope.argtypes = [vp, vp, vp, c_int, c_int, c_int, vp]
     L.svlm_vit_attn.argtypes = [vp, vp, c_int, vp, c_int, c_int, c_int, c_float, vp]
     L.svlm_gemm_bf16.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp]
@@ -119,7 +119,7 @@ def lib() -> ctypes.CDLL:
     L.svlm_qkv_rope_append_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, c_int64, c_int64, c_int64, c_int,
                                                vp, vp, vp, c_int, i32p, vp]
     L.svlm_attn_decode_streams.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, c_int, c_int, c_int, vp, c_size_t,
-                                           c_float, vp]
+                                           c_float, c_int, vp]
     L.svlm_kv_compact_rope_host.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int, vp, vp, c_int, i32p]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -202,12 +202,18 @@ def attn_workspace_bytes(n_q_tokens: int, q_heads: int, head_dim: int, num_split
     return int(lib().svlm_attn_workspace_bytes(n_q_tokens, q_heads, head_dim, num_splits))
 
 
+ATTN_EARLY_KV = 1
+
+
 def attn_causal(arena: ArenaView, buffer: int, layer: int, q, out, n_q_tokens: int, q_heads: int, kv_len: int, scale: float,
-                num_splits: int = 1, workspace=None, kv_len_dev=None):
+                num_splits: int = 1, workspace=None, kv_len_dev=None, early_kv: bool = False):
+    """`early_kv` (decode, with `kv_len_dev`): the device-side length and the cache rows below the one being appended were not written
+    by the launch right before this one -- the kernel may fetch them before its grid dependency resolves (SVLM_ATTN_EARLY_KV)."""
     _req_cuda(q, out)
     check(lib().svlm_attn_causal(arena.ref, buffer, layer, q.data_ptr(), out.data_ptr(), n_q_tokens, q_heads, kv_len,
                                  _ptr(kv_len_dev), num_splits, _ptr(workspace),
-                                 0 if workspace is None else workspace.numel() * workspace.element_size(), scale, _stream()),
+                                 0 if workspace is None else workspace.numel() * workspace.element_size(), scale,
+                                 ATTN_EARLY_KV if early_kv else 0, _stream()),
           "svlm_attn_causal")
 
 
@@ -381,12 +387,13 @@ def qkv_rope_append_streams(geometry: "ArenaView", slots, layer, q, k, v, q_head
                                              sin_table.data_ptr(), cos_table.shape[0], i32_array(section), _stream()), "svlm_qkv_rope_append_streams")
 
 
-def attn_decode_streams(geometry: "ArenaView", slots, layer, q, out, q_heads, max_kv_len, scale, num_splits, workspace):
+def attn_decode_streams(geometry: "ArenaView", slots, layer, q, out, q_heads, max_kv_len, scale, num_splits, workspace, early_kv: bool = False):
     _req_cuda(q, out)
     ws_ptr = workspace.data_ptr() if workspace is not None else None
     ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     check(lib().svlm_attn_decode_streams(geometry.ref, slots, len(slots), layer, q.data_ptr(), out.data_ptr(), q_heads, max_kv_len,
-                                         num_splits, ws_ptr, ws_bytes, scale, _stream()), "svlm_attn_decode_streams")
+                                         num_splits, ws_ptr, ws_bytes, scale, ATTN_EARLY_KV if early_kv else 0, _stream()),
+          "svlm_attn_decode_streams")
 
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)

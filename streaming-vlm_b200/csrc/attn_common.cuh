@@ -9,6 +9,6 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
                                     int rows, int D, int num_splits);
 
 int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
-                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st);
+                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, int flags, cudaStream_t st);
 
 }  // namespace svlm

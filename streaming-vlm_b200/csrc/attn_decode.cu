@@ -36,6 +36,7 @@ struct DecParams {
     const int32_t* kv_len_dev[SVLM_MAX_STREAMS];      // per stream (blockIdx.z)
     int rows_total;                                   // n_streams * Hq: row count of out / the partials
     int num_splits;
+    int early_kv;         // SVLM_ATTN_EARLY_KV: kv_len_dev and the K/V rows below kv_len - 1 are not outputs of the preceding launch
     int cluster;          // CTAs per cluster along the split axis: their partial (m, l, O) are merged through distributed shared memory
     int kv_head_base;
     uint16_t* out;        // bf16 [streams][Hq][D]           (num_splits == cluster: nothing left to merge)
@@ -130,9 +131,12 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh->tmem_base;
-    // everything above (barriers, TMEM, zeroed P^T) overlapped the tail of the QKV kernel; q, the new arena row and the
-    // device-side length are its outputs
-    pdl_wait();
+    // everything above (barriers, TMEM, zeroed P^T) overlapped the tail of the QKV kernel; q and the new arena row are its outputs.
+    // With SVLM_ATTN_EARLY_KV the caller guarantees that the device-side length and every row below kv_len - 1 are NOT: the length is
+    // read, and the K/V tiles that end below the new row are requested, before the grid dependency resolves -- the first TMA round
+    // trip of this latency-bound kernel overlaps the predecessor's tail.
+    const bool early = p.early_kv != 0;
+    if (!early) pdl_wait();
 
     // the host value is the documented upper bound (<= arena capacity): a device-side length beyond it never reaches the TMA
     const int kv_len = p.kv_len_dev[strm] ? min(__ldg(p.kv_len_dev[strm]), p.kv_len) : p.kv_len;
@@ -151,13 +155,30 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
     if (warp == 0) {
         // TMA producer: uniform control flow for the whole warp, one elected lane issues (same reason as the UMMA warp)
         if (n_tiles > 0) {
+            int u_pre = 0;
+            if (early) {
+                // tiles of this CTA that end at or below the row being appended (index kv_len - 1): immutable during this launch
+                const int safe_tiles = min(max((kv_len - 1) / DEC_BN - my_begin, 0), n_tiles);
+                u_pre = min(2 * safe_tiles, DEC_SLOTS);
+                for (int u = 0; u < u_pre; ++u) {                  // first use of every slot: nothing to wait for
+                    const int row = (my_begin + (u >> 1)) * DEC_BN;
+                    if (elect_one()) {
+                        const CUtensorMap* tm = (u & 1) ? &tmV : &tmK;
+                        mbar_arrive_expect_tx(&sh->full[u], DEC_TILE);
+                        tma_load_3d(sKV + u * DEC_TILE, tm, &sh->full[u], 0, row, kv_coord);
+                        tma_load_3d(sKV + u * DEC_TILE + DEC_PANEL, tm, &sh->full[u], 64, row, kv_coord);
+                    }
+                    __syncwarp();
+                }
+                pdl_wait();
+            }
             if (elect_one()) {
                 mbar_arrive_expect_tx(&sh->q_full, 2 * DEC_QP_PANEL);
                 tma_load_3d(sQ, &tmQ, &sh->q_full, 0, head * G, strm);
                 tma_load_3d(sQ + DEC_QP_PANEL, &tmQ, &sh->q_full, 64, head * G, strm);
             }
             __syncwarp();
-            for (int u = 0; u < 2 * n_tiles; ++u) {
+            for (int u = u_pre; u < 2 * n_tiles; ++u) {
                 const int s = u % DEC_SLOTS;
                 const int row = (my_begin + (u >> 1)) * DEC_BN;
                 mbar_wait(&sh->empty[s], ((u / DEC_SLOTS) & 1) ^ 1);
@@ -171,6 +192,7 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
             }
         }
     } else if (warp == 1) {
+        if (early) pdl_wait();
         // UMMA issuer.  The whole warp walks the loop (uniform control flow and operands, so the descriptors live in
         // uniform registers); one elected lane issues.  A divergent `if (lane == 0)` around the loop makes ptxas wrap every
         // tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall (~100 cycles per instruction, measured).
@@ -230,6 +252,7 @@ attn_decode_kernel(const __grid_constant__ DecMaps maps, const DecParams p) {
             }
         }
     } else {
+        if (early) pdl_wait();
         // ---- softmax: thread = one key of the tile; epilogue: thread = one head-dim lane of O^T
         const int q4 = warp & 3;
         const int row = q4 * 32 + lane;
@@ -489,7 +512,7 @@ static void* getenv_ptr(const char* name) {
 // Shared by the single-stream entry (svlm_attn_causal with Tq = 1) and svlm_attn_decode_streams.
 static int decode_launch_common(const svlm_arena_t* geom, const void* const* arena_base, const int* buffer, const int32_t* const* kv_len_dev,
                                 int n_streams, int layer, const void* q, void* out, int q_heads, int kv_len, int num_splits,
-                                void* workspace, float scale, cudaStream_t st) {
+                                void* workspace, float scale, int flags, cudaStream_t st) {
     const int D = geom->head_dim, H = geom->kv_heads, G = q_heads / H;
     ArenaDims ad{geom->layers, H, D, geom->capacity};
     static thread_local DecMaps maps;
@@ -512,6 +535,7 @@ static int decode_launch_common(const svlm_arena_t* geom, const void* const* are
     }
     p.Hq = q_heads; p.G = G; p.D = D;
     p.kv_len = kv_len; p.num_splits = num_splits;
+    p.early_kv = (flags & SVLM_ATTN_EARLY_KV) ? 1 : 0;
     // Splits of one (stream, kv head) that sit in one thread-block cluster merge through distributed shared memory (push based, see the
     // kernel): no merge launch, no fp32 round trip of the partials.  Measured on B200 (benchmarks/decode_attn_cluster_sweep.py,
     // profiles/r2k_decode_cluster_push_sweep.jsonl): for the few splits of the multi-stream launch (4 per stream and head) it wins;
@@ -550,9 +574,10 @@ static int decode_launch_common(const svlm_arena_t* geom, const void* const* are
 }
 
 int attn_decode_launch(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int q_heads, int kv_len,
-                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, cudaStream_t st) {
+                       const int32_t* kv_len_dev, int num_splits, void* workspace, float scale, int flags, cudaStream_t st) {
     const void* base = arena->base;
-    return decode_launch_common(arena, &base, &buffer, &kv_len_dev, 1, layer, q, out, q_heads, kv_len, num_splits, workspace, scale, st);
+    return decode_launch_common(arena, &base, &buffer, &kv_len_dev, 1, layer, q, out, q_heads, kv_len, num_splits, workspace, scale,
+                                kv_len_dev ? flags : 0, st);
 }
 
 }  // namespace svlm
@@ -561,7 +586,7 @@ using namespace svlm;
 
 extern "C" int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm_stream_slot_t* slots, int n_streams, int layer,
                                         const void* q, void* out, int q_heads, int max_kv_len, int num_splits, void* workspace,
-                                        size_t workspace_bytes, float scale, void* stream) {
+                                        size_t workspace_bytes, float scale, int flags, void* stream) {
     int rc = check_device();
     if (rc) return rc;
     SVLM_REQUIRE(geometry && slots && q && out, "NULL argument");
@@ -586,5 +611,5 @@ extern "C" int svlm_attn_decode_streams(const svlm_arena_t* geometry, const svlm
         base[b] = slots[b].arena_base; buffer[b] = slots[b].buffer; kvl[b] = slots[b].kv_len_dev;
     }
     return decode_launch_common(geometry, base, buffer, kvl, n_streams, layer, q, out, q_heads, max_kv_len, num_splits, workspace, scale,
-                                (cudaStream_t)stream);
+                                flags, (cudaStream_t)stream);
 }

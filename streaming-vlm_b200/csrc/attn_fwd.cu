@@ -505,7 +505,7 @@ extern "C" size_t svlm_attn_workspace_bytes(int n_q_tokens, int q_heads, int hea
 
 extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer, const void* q, void* out, int n_q_tokens, int q_heads,
                                 int kv_len, const int32_t* kv_len_dev, int num_splits, void* workspace, size_t workspace_bytes,
-                                float scale, void* stream) {
+                                float scale, int flags, void* stream) {
     int rc = check_device();
     if (rc) return rc;
     if ((rc = validate_arena(arena))) return rc;
@@ -522,7 +522,8 @@ extern "C" int svlm_attn_causal(const svlm_arena_t* arena, int buffer, int layer
     const size_t need = svlm_attn_workspace_bytes(n_q_tokens, q_heads, D, num_splits);
     SVLM_REQUIRE(num_splits == 1 || (workspace != nullptr && workspace_bytes >= need), "workspace too small: need %zu bytes", need);
     if (n_q_tokens == 1 && G <= 8)    // decode: swap-AB kernel (attn_decode.cu)
-        return attn_decode_launch(arena, buffer, layer, q, out, q_heads, kv_len, kv_len_dev, num_splits, workspace, scale, (cudaStream_t)stream);
+        return attn_decode_launch(arena, buffer, layer, q, out, q_heads, kv_len, kv_len_dev, num_splits, workspace, scale, flags,
+                                  (cudaStream_t)stream);
 
     ArenaDims ad{arena->layers, H, D, arena->capacity};
     const uint16_t* base = (const uint16_t*)arena->base;

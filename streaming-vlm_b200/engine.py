@@ -209,6 +209,7 @@ class StreamingEngine:
         self._side = torch.cuda.Stream(device=dev)
         self._prefetch_gu_bytes = int(float(os.environ.get("SVLM_DECODE_PREFETCH_MB", "16")) * (1 << 20))
         self._prefetch = os.environ.get("SVLM_DECODE_PREFETCH", "1") != "0"
+        self._early_kv = os.environ.get("SVLM_ATTN_EARLY_KV", "1") != "0"
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
         self._dec_part = torch.zeros(g.hidden, dtype=torch.bfloat16, device=dev)
@@ -607,8 +608,10 @@ class StreamingEngine:
                     _abi.prefetch_l2(L["wo"])
                     if self._prefetch_gu_bytes:
                         _abi.prefetch_l2(L["wgu"], self._prefetch_gu_bytes)
+            # early_kv: the counters were advanced at the end of the previous token and the launch right before this one appends
+            # row kv_len - 1 only, so the attention kernel may fetch the older K/V tiles before its grid dependency resolves
             _abi.attn_causal(c.view, c.cur, li, q_rot, o, 1, hq, c.capacity, self.scale, self._splits_now,
-                             self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev)
+                             self.ws if self._splits_now > 1 else None, kv_len_dev=self.kv_after_dev, early_kv=self._early_kv)
             if self._prefetch:
                 main.wait_stream(self._side)
             if self.tp is None:

@@ -102,7 +102,7 @@ class MultiStreamEngine:
             _abi.gemm_tokens_qkv_append(c0.view, slots, li, x, L["wqkv"], L["bqkv"], L["ln1"], g.rms_eps, hq, self._q_rot, c0.cos_table,
                                         c0.sin_table, stats_in=st_mlp if li else None)
             _abi.attn_decode_streams(c0.view, slots, li, self._q_rot, self._o, hq, c0.capacity, e0.scale, splits,
-                                     self.ws if splits > 1 else None)
+                                     self.ws if splits > 1 else None, early_kv=e0._early_kv)
             _abi.gemm_tokens(self._o.view(B, -1), L["wo"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_attn)
             _abi.gemm_tokens(x, L["wgu"], act, epilogue=_abi.EPI_SWIGLU, norm_weight=L["ln2"], eps=g.rms_eps, stats_in=st_attn)
             _abi.gemm_tokens(act, L["wd"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_mlp)
@@ -133,7 +133,7 @@ class MultiStreamEngine:
             q, k, v = qkv[:, :hq * d], qkv[:, hq * d:(hq + hkv) * d], qkv[:, (hq + hkv) * d:]
             _abi.qkv_rope_append_streams(c0.view, slots, li, q, k, v, hq, self._q_rot, c0.cos_table, c0.sin_table, c0.section)
             _abi.attn_decode_streams(c0.view, slots, li, self._q_rot, self._o, hq, c0.capacity, e0.scale, splits,
-                                     self.ws if splits > 1 else None)
+                                     self.ws if splits > 1 else None, early_kv=e0._early_kv)
             x, h = e0._add_norm(x, F.linear(self._o.view(B, -1), L["wo"]), L["ln2"], g.rms_eps)
             pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
         logits = e0._logits(x, pending)                                   # [B, vocab] fp32, suppressed ids at -inf

@@ -928,3 +928,48 @@ def test_gemm_tokens_statistics_hand_off(abi, t, hidden, mlp):
     torch.testing.assert_close(got.float(), want.float(), rtol=1.6e-2, atol=1e-2)
     frac = (bits(got.cpu()) != bits(want.cpu())).float().mean().item()
     assert frac < 0.02, f"{frac:.4f} of the outputs differ from the unfused chain"
+
+
+@pytest.mark.parametrize("kv_after,splits", [(5789, 23), (129, 1), (128, 1), (257, 2), (256, 2), (1, 1), (4097, 16), (6000, 8)])
+def test_attn_decode_early_kv_prefetch_is_bit_identical(abi, tables, kv_after, splits):
+    """SVLM_ATTN_EARLY_KV: the decode attention reads the device-side length and requests the K/V tiles below the row being appended
+    BEFORE its grid dependency resolves.  In the real chain (q/k/v GEMV appending row kv_len - 1 right before it, programmatic
+    dependent launch, CUDA-graph replay) the result must equal the launch without the flag bit for bit -- including lengths whose
+    new row is the first / last row of a tile, where the tile holding it must NOT be fetched early."""
+    L, H, cap, Hq, hidden = 2, 4, 6144, 28, 3584
+    g = torch.Generator().manual_seed(kv_after)
+    w = (torch.randn((Hq + 2 * H) * 128, hidden, generator=g) / math.sqrt(hidden)).to(torch.bfloat16).to(DEV)
+    b = (torch.randn((Hq + 2 * H) * 128, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.1 * torch.randn(hidden, generator=g)).to(torch.bfloat16).to(DEV)
+    cos, sin = (t.to(DEV) for t in tables)
+    row = torch.tensor([kv_after - 1], dtype=torch.int32, device=DEV)
+    after = torch.tensor([kv_after], dtype=torch.int32, device=DEV)
+    pos = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    outs = []
+    for early in (False, True):
+        _, arena, view = make_arena(abi, L, H, cap, seed=7)
+        q_rot = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+        o = torch.zeros(1, Hq, 128, dtype=torch.bfloat16, device=DEV)
+        ws = torch.zeros(abi.attn_workspace_bytes(1, Hq, 128, splits) // 4 + 16, dtype=torch.float32, device=DEV) if splits > 1 else None
+        xs = [torch.randn(hidden, generator=torch.Generator().manual_seed(100 + i)).to(torch.bfloat16).to(DEV) for i in range(3)]
+
+        def chain(x):
+            abi.gemv_qkv_rope_append(view, 0, 1, w, x, nw, 1e-6, b, Hq, q_rot, row, pos, cos, sin)
+            abi.attn_causal(view, 0, 1, q_rot, o, 1, Hq, cap, 1.0 / math.sqrt(128), splits, ws, kv_len_dev=after, early_kv=early)
+        chain(xs[0])
+        torch.cuda.synchronize()
+        graphs = []
+        for x in xs:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                chain(x)
+            graphs.append(gr)
+        res = []
+        for _ in range(3):                      # every replay rewrites row kv_after - 1 with another token's K/V just before attending
+            for gr in graphs:
+                gr.replay()
+                res.append(o.clone())
+        torch.cuda.synchronize()
+        outs.append(torch.stack(res).cpu())
+    assert torch.equal(bits(outs[0]), bits(outs[1]))
+    assert not torch.equal(bits(outs[0][0]), bits(outs[0][1]))          # the appended row matters (different tokens, different outputs)
