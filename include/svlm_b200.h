@@ -360,6 +360,18 @@ int svlm_tp_allreduce_rows(const svlm_tp_ctx_t* ctx, int which, const void* resi
 int svlm_prefetch_l2(const void* ptr, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Host helper (no device work, usable without a GPU): the token-pattern scan behind
+ * `get_qwen_range` (utils/get_qwen_range.py:15-86), which `process_past_kv` (inference/inference.py:91-170) runs five times per
+ * chunk over the ~5.8k ids of the stream.  Segments are found left to right and never overlap: a segment starts where `pattern`
+ * (1..8 tokens) matches and ends at the first `end_token` at or after the end of the pattern -- a start without a terminator ends the
+ * scan --; a trailing `lf_token` is absorbed when `contain_lf`.  `index` >= 0 counts from the left, < 0 (down to -256) from the right.
+ * Writes the closed interval to *start_out / *end_out and, if count_out != NULL, the number of segments seen (all of them for a
+ * negative index).  SVLM_EINVAL when the index is out of range (the reference raises IndexError).
+ * ------------------------------------------------------------------------------------- */
+int svlm_find_segment(const int64_t* ids, int64_t n, const int64_t* pattern, int pattern_len, int64_t end_token, int index,
+                      int contain_lf, int64_t lf_token, int64_t* start_out, int64_t* end_out, int64_t* count_out);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (the reference-facing plugin call with HOST data):
  * copy in, run, copy out, synchronise.  Used by bench.py's end-to-end leg and by callers that
  * keep the cache in host memory.

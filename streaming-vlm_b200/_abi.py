@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
            "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex", "svlm_gemm_tokens", "svlm_gemm_tokens_qkv_append",
-           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
+           "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_find_segment", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
            "svlm_frames_to_patches", "svlm_frames_resize_bicubic", "svlm_tp_gemv_allreduce", "svlm_tp_allreduce_rows",
            "svlm_kv_compact_rope_host"]
 
@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
     L.svlm_mark_seen.argtypes = [vp, c_int, vp, c_int64, c_int, vp]
     L.svlm_embed_tokens.argtypes = [vp, c_int, c_int64, vp, c_int64, vp, c_int, c_int, vp, vp, vp]
     L.svlm_prefetch_l2.argtypes = [vp, c_size_t, vp]
+    L.svlm_find_segment.argtypes = [vp, c_int64, POINTER(c_int64), c_int, c_int64, c_int, c_int, c_int64, POINTER(c_int64), POINTER(c_int64),
+                                    POINTER(c_int64)]
     L.svlm_tp_gemv_allreduce.argtypes = [POINTER(TpCtx), c_int, vp, vp, vp, vp, c_int, c_int, vp]
     L.svlm_tp_allreduce_rows.argtypes = [POINTER(TpCtx), c_int, vp, vp, c_int, c_int, vp]
     L.svlm_frames_resize_bicubic.argtypes = [vp, c_int, c_int, c_int, vp, c_int, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp]
@@ -361,6 +363,18 @@ def tp_allreduce_rows(ctx_ref, which: int, residual, out, rows: int, cols: int):
     """out = residual + bf16(sum over ranks of the bf16 partial products sitting in region `which` of the symmetric buffer)."""
     _req_cuda(residual, out)
     check(lib().svlm_tp_allreduce_rows(ctx_ref, which, residual.data_ptr(), out.data_ptr(), rows, cols, _stream()), "svlm_tp_allreduce_rows")
+
+
+def find_segment(ids_np, pattern, end_token: int, index: int, contain_lf: bool, lf_token: int):
+    """(start, end) of the `index`-th non-overlapping segment `pattern ... end_token` in a contiguous int64 numpy array: the native
+    scan behind `get_qwen_range` (include/svlm_b200.h, svlm_find_segment; host only, no GPU needed).  IndexError when out of range."""
+    pat = (c_int64 * len(pattern))(*pattern)
+    s, e = c_int64(0), c_int64(0)
+    rc = lib().svlm_find_segment(ids_np.ctypes.data, ids_np.shape[0], pat, len(pattern), end_token, index, 1 if contain_lf else 0, lf_token,
+                                 ctypes.byref(s), ctypes.byref(e), None)
+    if rc != 0:
+        raise IndexError(lib().svlm_last_error().decode(errors="replace"))
+    return s.value, e.value
 
 
 def make_slots(caches, row_devs, pos_devs, kv_len_devs):

@@ -142,3 +142,51 @@ int svlm_kv_compact_rope_host(void* arena_host, int layers, int kv_heads, int he
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Host-side token-pattern range finder (no device work): the scan behind `get_qwen_range` (reference utils/get_qwen_range.py:15-86),
+// which the eviction planner calls five times per chunk.  One pass over the ids: a segment starts where `pattern` matches, ends at the
+// first `end_token` at or after the end of the pattern (a start without a terminator ends the scan), the next search begins behind it;
+// a trailing `lf_token` is absorbed when `contain_lf`.  `index` counts from the left (>= 0) or from the right (< 0).
+// ---------------------------------------------------------------------------------------------------------------------------------
+extern "C" int svlm_find_segment(const int64_t* ids, int64_t n, const int64_t* pattern, int pattern_len, int64_t end_token, int index,
+                                 int contain_lf, int64_t lf_token, int64_t* start_out, int64_t* end_out, int64_t* count_out) {
+    SVLM_REQUIRE(ids != nullptr || n == 0, "ids is NULL");
+    SVLM_REQUIRE(pattern != nullptr && pattern_len >= 1 && pattern_len <= 8, "pattern of 1..8 tokens expected");
+    SVLM_REQUIRE(start_out && end_out, "NULL output pointer");
+    const int m = pattern_len;
+    // segments are found left to right; for index >= 0 the scan stops at that one, for index < 0 a ring of the last -index is kept
+    const int keep = index < 0 ? -index : 1;
+    SVLM_REQUIRE(keep <= 256, "index %d out of the supported range (-256 .. )", index);
+    int64_t ring_s[256], ring_e[256];
+    int64_t count = 0, i = 0;
+    bool found = false;
+    while (i + m <= n) {
+        if (ids[i] != pattern[0]) { ++i; continue; }
+        bool match = true;
+        for (int j = 1; j < m; ++j)
+            if (ids[i + j] != pattern[j]) { match = false; break; }
+        if (!match) { ++i; continue; }
+        int64_t e = i + m;
+        while (e < n && ids[e] != end_token) ++e;
+        if (e >= n) break;                                       // no terminator: the scan ends here (reference :80-81)
+        int64_t stop = e;
+        if (contain_lf && e + 1 < n && ids[e + 1] == lf_token) stop = e + 1;
+        ring_s[count % keep] = i;
+        ring_e[count % keep] = stop;
+        ++count;
+        if (index >= 0 && count == (int64_t)index + 1) { found = true; break; }
+        i = e + 1;                                               // non-overlapping: the absorbed line feed may start nothing anyway
+    }
+    if (count_out) *count_out = count;
+    if (index >= 0) {
+        SVLM_REQUIRE(found, "segment index %d out of range (%lld segments)", index, (long long)count);
+        *start_out = ring_s[(count - 1) % keep];
+        *end_out = ring_e[(count - 1) % keep];
+    } else {
+        SVLM_REQUIRE(count >= keep, "segment index %d out of range (%lld segments)", index, (long long)count);
+        *start_out = ring_s[(count - keep) % keep];
+        *end_out = ring_e[(count - keep) % keep];
+    }
+    return SVLM_OK;
+}

@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..utils.get_qwen_range import TOKEN_IDS, as_host_ids, find_segments
+from ..utils.get_qwen_range import TOKEN_IDS, as_host_ids, find_segment
 
 DEFAULT_WINDOW_SIZE = 16
 DEFAULT_TEXT_ROUND = 16
@@ -33,7 +33,7 @@ class EvictionPlan:
         self.src = np.arange(self.ids.shape[0], dtype=np.int64)
 
     def _range(self, label, index, contain_lf=True):
-        s, e = find_segments(self.ids, label, contain_lf)[index]
+        s, e = find_segment(self.ids, label, index, contain_lf)
         return (s, e - 1) if label == "user_text" else (s, e)
 
     def delete(self, a: int, b: int):

@@ -98,6 +98,46 @@ def test_find_segments_equals_oracle_on_random_token_soups():
     check()
 
 
+def test_native_find_segment_equals_vectorised_scan_and_oracle():
+    """`svlm_find_segment` (host function of the C ABI, what the planner calls) against the numpy scan and the oracle's sequential
+    restatement: every label, both `contain_lf` settings, every valid index from both ends, IndexError beyond them -- on random token
+    soups (nested, unterminated, overlapping patterns) and on a long steady-state stream."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import tokens as o_tok
+    from streaming_vlm_b200 import synthetic
+    from streaming_vlm_b200.utils.get_qwen_range import TOKEN_IDS, find_segment, find_segments
+    alphabet = [TOKEN_IDS["<|im_start|>"], TOKEN_IDS["<|im_end|>"], TOKEN_IDS["user"], TOKEN_IDS["assistant"], TOKEN_IDS["Time"],
+                TOKEN_IDS["\n"], TOKEN_IDS["<|vision_start|>"], TOKEN_IDS["<|vision_end|>"], TOKEN_IDS["<|video_pad|>"],
+                *TOKEN_IDS["previous text"], 1000, 1001]
+
+    def compare(ids_list):
+        arr = np.asarray(ids_list, dtype=np.int64)
+        for label in ("user", "previous text", "user_text", "assistant", "vision"):
+            for lf in (True, False):
+                want = [tuple(x) for x in o_tok.all_ranges(list(ids_list), label, lf)]
+                assert find_segments(arr, label, lf) == want
+                n = len(want)
+                for index in list(range(n)) + list(range(-n, 0)):
+                    assert find_segment(arr, label, index, lf) == want[index], (label, lf, index)
+                for index in (n, -n - 1):
+                    with pytest.raises(IndexError):
+                        find_segment(arr, label, index, lf)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.sampled_from(alphabet), min_size=0, max_size=60))
+    def check(ids):
+        compare(ids)
+
+    check()
+    st_ = synthetic.fast_forward(40, new_tokens=20, seed=3)
+    ids = np.asarray(st_["prev_ids"], dtype=np.int64)
+    for label in ("user", "previous text", "user_text", "assistant", "vision"):
+        segs = find_segments(ids, label, True)
+        assert len(segs) >= 1
+        for index in (0, -1, len(segs) // 2, -len(segs)):
+            assert find_segment(ids, label, index, True) == segs[index]
+
+
 def test_planner_equals_oracle_on_random_policies():
     """Product planner (`plan_past_kv`, numpy) against the oracle's `plan_eviction` (pinned on five policies) over 40 RANDOM
     policies -- window, text rounds, sink and sliding-window sizes, turn lengths, early <|im_end|> -- 24 rounds each: pruned ids
