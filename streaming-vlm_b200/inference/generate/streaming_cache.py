@@ -86,6 +86,12 @@ class StreamingCache:
         self.seq_len = 0
         self._seen_tokens = 0
         self.section = tuple(geo.mrope_section)
+        # The kernels clamp a position to the last table row instead of reading beyond it, which would rotate with the wrong angle
+        # silently: the host rules that out.  "shrink" positions never exceed the number of cached tokens (<= capacity), so the table
+        # must cover the capacity; "append" positions grow for ever and are checked as they are handed out (reserve_positions).
+        if max_position is not None and int(max_position) < self.capacity:
+            raise ValueError(f"max_position {max_position} is smaller than the arena capacity {self.capacity}: contiguous positions "
+                             "reach the capacity, the rotary tables must cover them")
         self.cos_table, self.sin_table = rope_tables(geo, max_position or self.capacity, self.device)
         self.pos = torch.zeros(3, self.capacity, dtype=torch.int32, device=self.device)
         self.next_pos = torch.zeros(1, dtype=torch.int32, device=self.device)
