@@ -111,7 +111,8 @@ class MultiStreamEngine:
         logits = logits.float()
         if e0.suppress is not None:
             logits = logits.masked_fill(e0.suppress, float("-inf"))
-        self.launches += g.num_layers * (5 + (1 if splits > 1 else 0)) + 1
+        merged_in_cluster = splits in (2, 4, 8)                # the batched attention merges these split counts inside clusters: no merge launch
+        self.launches += g.num_layers * (5 + (1 if splits > 1 and not merged_in_cluster else 0)) + 1
         self._advance(torch.argmax(logits, dim=-1))
 
     def _advance(self, nxt):
@@ -138,7 +139,7 @@ class MultiStreamEngine:
             pending = F.linear(e0._swiglu(F.linear(h, L["wgu"]), g.mlp), L["wd"])
         logits = e0._logits(x, pending)                                   # [B, vocab] fp32, suppressed ids at -inf
         self._advance(torch.argmax(logits, dim=-1))
-        self.launches += (e0.launches - before) + g.num_layers * (2 + (1 if splits > 1 else 0))
+        self.launches += (e0.launches - before) + g.num_layers * (2 + (1 if splits > 1 and splits not in (2, 4, 8) else 0))
         e0.launches = before
 
     def decode_step(self, done=None):
