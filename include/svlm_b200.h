@@ -15,7 +15,8 @@
  *   - return value: 0 on success, a negative SVLM_E* code otherwise; `svlm_last_error()`
  *     returns a thread-local, human-readable message for the last failure;
  *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry
- *     point returns SVLM_ENODEV.
+ *     point returns SVLM_ENODEV (svlm_find_segment, a host-only helper of the eviction planner,
+ *     is the one function that does no device work).
  *
  * KV arena (one per video stream, owned by the caller, e.g. a torch tensor):
  *   bf16 [2 buffers][3 planes][L layers][H_kv][cap tokens][D]
