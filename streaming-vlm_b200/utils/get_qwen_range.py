@@ -91,6 +91,8 @@ def find_segment(ids: np.ndarray, label: str, index: int, contain_lf: bool = Tru
     assert label in _LABELS, label
     from .. import _abi
     pat, end_tok = _LABELS[label]
+    if index < -256:                      # beyond the native scan's ring of trailing segments: the vectorised scan answers
+        return find_segments(ids, label, contain_lf)[index]
     ids = np.ascontiguousarray(ids, dtype=np.int64)
     return _abi.find_segment(ids, pat, end_tok, index, contain_lf, TOKEN_IDS["\n"])
 
