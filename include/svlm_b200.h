@@ -193,6 +193,18 @@ int svlm_gemm_bf16_ex(const void* A, const void* W, const void* bias, const void
 int svlm_gemm_tokens(const void* X, const void* W, const void* bias, const void* residual, void* Y, int T, int N, int K,
                      int epilogue, int splits, const void* norm_weight, float eps, const float* stats_in, int stats_tiles,
                      float* stats_out, void* stream);
+/* lm_head of the batched decode step without a logits tensor (final norm + `lm_head` + `suppress_tokens` + argmax, qwen2_5/
+ * model_forward.py:316-317 and generate/streaming_generate_qwen.py:96-99 for greedy decoding): per token t < T <= 16, keys[t] receives
+ * max over the vocabulary rows n that are not suppressed of (ordered bf16 logit << 32 | 0xffffffff - n), i.e. the FIRST index of the
+ * maximum logit, exactly torch.argmax over `lm_head(h).float().masked_fill(suppress, -inf)`.  keys must be zero on entry
+ * (svlm_streams_advance clears them).  norm_weight / stats_in as in svlm_gemm_tokens. */
+int svlm_gemm_tokens_lm_head_argmax(const void* X, const void* W, const void* norm_weight, float eps, const float* stats_in,
+                                    int stats_tiles, const uint8_t* suppress, int T, int N, int K, unsigned long long* keys,
+                                    void* stream);
+/* End of a batched decode step: stream b takes the id selected in keys[b] and advances its device-side counters if active[b] != 0
+ * (tok, kv_len += 1, next_pos += 1); kv_after[b] = kv_len[b] + 1 for every stream; keys are cleared. */
+int svlm_streams_advance(unsigned long long* keys, int64_t* tok, const int32_t* active, int32_t* kv_len, int32_t* kv_after,
+                         int32_t* next_pos, int n_streams, void* stream);
 int svlm_rmsnorm(const void* x, const void* weight, void* out, int rows, int cols, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ["svlm_version", "svlm_last_error", "svlm_kv_compact_rope", "svlm_mrope_positions", "svlm_qkv_rope_append",
-           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex", "svlm_gemm_tokens", "svlm_gemm_tokens_qkv_append",
+           "svlm_attn_workspace_bytes", "svlm_attn_causal", "svlm_vit_rope", "svlm_vit_attn", "svlm_gemm_bf16", "svlm_gemm_bf16_ex", "svlm_gemm_tokens", "svlm_gemm_tokens_qkv_append", "svlm_gemm_tokens_lm_head_argmax", "svlm_streams_advance",
            "svlm_rmsnorm", "svlm_add_rmsnorm", "svlm_swiglu", "svlm_gemv_bf16", "svlm_gemv_qkv_rope_append", "svlm_lm_head_argmax", "svlm_lm_head_sample", "svlm_mark_seen", "svlm_embed_tokens", "svlm_prefetch_l2", "svlm_find_segment", "svlm_qkv_rope_append_streams", "svlm_attn_decode_streams",
            "svlm_frames_to_patches", "svlm_frames_resize_bicubic", "svlm_tp_gemv_allreduce", "svlm_tp_allreduce_rows",
            "svlm_kv_compact_rope_host"]
@@ -102,6 +102,8 @@ def lib() -> ctypes.CDLL:
     L.svlm_gemm_tokens.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, c_float, vp, c_int, vp, vp]
     L.svlm_gemm_tokens_qkv_append.argtypes = [POINTER(Arena), POINTER(StreamSlot), c_int, c_int, vp, vp, vp, vp, c_float, vp, c_int, c_int, c_int,
                                               vp, vp, vp, c_int, c_int, vp]
+    L.svlm_gemm_tokens_lm_head_argmax.argtypes = [vp, vp, vp, c_float, vp, c_int, vp, c_int, c_int, c_int, vp, vp]
+    L.svlm_streams_advance.argtypes = [vp, vp, vp, vp, vp, vp, c_int, vp]
     L.svlm_rmsnorm.argtypes = [vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_float, vp]
     L.svlm_swiglu.argtypes = [vp, vp, c_int, c_int, c_int64, c_int64, vp]
@@ -286,6 +288,25 @@ def gemm_tokens_qkv_append(geometry: "ArenaView", slots, layer, x, w, bias, norm
                                             eps, _ptr(stats_in), 0 if stats_in is None else stats_in.shape[0], q_heads, x.shape[1],
                                             q_rot.data_ptr(), cos_table.data_ptr(), sin_table.data_ptr(),
                                             cos_table.shape[0], splits, _stream()), "svlm_gemm_tokens_qkv_append")
+
+
+def gemm_tokens_lm_head_argmax(x, w, keys, norm_weight=None, eps: float = 1e-6, stats_in=None, suppress_u8=None):
+    """keys[t] = packed (logit, ~row) maximum over the non-suppressed rows of norm(x)[t] @ w.T: the batched lm_head + argmax without a
+    logits tensor (include/svlm_b200.h, svlm_gemm_tokens_lm_head_argmax).  `keys`: int64 / uint64 [T], zero on entry."""
+    _req_cuda(x, w, keys, norm_weight, stats_in, suppress_u8)
+    t, k = x.shape
+    assert w.shape[1] == k and x.is_contiguous() and w.is_contiguous() and keys.numel() >= t and keys.element_size() == 8
+    assert suppress_u8 is None or (suppress_u8.dtype == torch.uint8 and suppress_u8.numel() == w.shape[0])
+    check(lib().svlm_gemm_tokens_lm_head_argmax(x.data_ptr(), w.data_ptr(), _ptr(norm_weight), eps, _ptr(stats_in),
+                                                0 if stats_in is None else stats_in.shape[0], _ptr(suppress_u8), t, w.shape[0], k,
+                                                keys.data_ptr(), _stream()), "svlm_gemm_tokens_lm_head_argmax")
+
+
+def streams_advance(keys, tok, active, kv_len, kv_after, next_pos):
+    _req_cuda(keys, tok, active, kv_len, kv_after, next_pos)
+    assert tok.dtype == torch.int64 and all(t_.dtype == torch.int32 for t_ in (active, kv_len, kv_after, next_pos))
+    check(lib().svlm_streams_advance(keys.data_ptr(), tok.data_ptr(), active.data_ptr(), kv_len.data_ptr(), kv_after.data_ptr(),
+                                     next_pos.data_ptr(), tok.numel(), _stream()), "svlm_streams_advance")
 
 
 def interleave_gate_up(gate, up, block: int = 64):

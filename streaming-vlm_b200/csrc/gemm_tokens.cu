@@ -38,7 +38,7 @@ constexpr int TOK_MAX_STAGES = 12;
 constexpr int TOK_MAX_SPLITS = 8;
 constexpr int TOK_MAX_STAT_TILES = 64;            // statistics hand-off: producer row tiles (hidden <= 8192)
 
-enum { TOK_EPI_NONE = 0, TOK_EPI_RESIDUAL = 2, TOK_EPI_SWIGLU = 3, TOK_EPI_QKV_APPEND = 4 };
+enum { TOK_EPI_NONE = 0, TOK_EPI_RESIDUAL = 2, TOK_EPI_SWIGLU = 3, TOK_EPI_QKV_APPEND = 4, TOK_EPI_ARGMAX = 5 };
 
 struct TokAppend {                                   // TOK_EPI_QKV_APPEND
     uint16_t* buf[SVLM_MAX_STREAMS];                 // live buffer of each stream's arena
@@ -67,6 +67,8 @@ struct TokParams {
     const float* stats_in;      // RMSNorm prologue: per-(row tile of the producer, token) sums of squares of X (stats_tiles x T), or NULL
     int stats_tiles;
     float* stats_out;           // residual epilogue: the same for the rows of Y this tile wrote ([tiles][T]), or NULL
+    const uint8_t* suppress;    // TOK_EPI_ARGMAX: rows (vocabulary ids) that are never selected, or NULL
+    unsigned long long* keys;   // TOK_EPI_ARGMAX: per token, max over rows of (ordered bf16 logit << 32 | ~row): first index of the maximum
 };
 
 struct TokShared {
@@ -77,6 +79,7 @@ struct TokShared {
     float red[4][4];
     float stat[16][4];
     float stage_stats[TOK_MAX_STAT_TILES * 16];
+    unsigned long long best[16][4];
 };
 
 __device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
@@ -87,6 +90,10 @@ __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.c
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // the four epilogue warps
 __device__ __forceinline__ float bf16_at(const uint16_t* p) { return __uint_as_float((uint32_t)__ldg(p) << 16); }
 __device__ __forceinline__ uint16_t to_bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ uint32_t tok_ordered_f32(float f) {      // monotonic float -> uint32 map
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 template <int TN>
 __device__ __forceinline__ void tok_load_acc(uint32_t taddr, float (&v)[TN]) {
@@ -424,6 +431,33 @@ gemm_tokens_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     }
                 }
             }
+        } else if (p.epi == TOK_EPI_ARGMAX) {
+            if constexpr (TN == 16) {
+                // lm_head of the batched decode step: no logits tensor -- per token the first index of the maximum bf16 logit over
+                // the rows that are not suppressed (torch.argmax of `lm_head(h).float().masked_fill(suppress, -inf)`): warp maximum,
+                // four warp maxima through shared memory, ONE atomicMax per token and tile on a packed (value, ~row) key
+                const int n = tile * 128 + row;
+                const bool ok = n < p.N && !(p.suppress && p.suppress[n]);
+#pragma unroll
+                for (int t = 0; t < TN; ++t) {
+                    unsigned long long key = 0ull;
+                    if (ok && t < p.T)
+                        key = ((unsigned long long)tok_ordered_f32(round_bf16(v[t])) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+                        key = o > key ? o : key;
+                    }
+                    if (lane == 0) sh->best[t][q4] = key;
+                }
+                epi_bar_sync();
+                if (row < p.T) {
+                    unsigned long long key = sh->best[row][0];
+#pragma unroll
+                    for (int w = 1; w < 4; ++w) key = sh->best[row][w] > key ? sh->best[row][w] : key;
+                    if (key) atomicMax(p.keys + row, key);
+                }
+            }
         } else {
             const int n = tile * 128 + row;
             const float b = (p.bias && n < p.N) ? bf16_at(p.bias + n) : 0.f;
@@ -500,6 +534,26 @@ static int launch_tokens(const CUtensorMap& tx, const CUtensorMap& tw, const Tok
     return launch_status("gemm_tokens_kernel");
 }
 
+// Token ids and device-side counters of the batched decode loop, from the keys the lm_head launch left: stream b takes the selected id
+// and advances its kv length / next text position if it is ACTIVE (a stream whose turn has ended keeps its state); kv_after = kv_len + 1
+// for every stream; the keys are cleared for the next step.
+__global__ void streams_advance_kernel(unsigned long long* keys, int64_t* tok, const int32_t* active, int32_t* kv_len, int32_t* kv_after,
+                                       int32_t* next_pos, int n_streams) {
+    pdl_wait();
+    const int b = threadIdx.x;
+    if (b >= n_streams) return;
+    const unsigned long long k = keys[b];
+    keys[b] = 0ull;
+    int n = kv_len[b];
+    if (active[b]) {
+        tok[b] = (int64_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+        n += 1;
+        kv_len[b] = n;
+        next_pos[b] = next_pos[b] + 1;
+    }
+    kv_after[b] = n + 1;
+}
+
 // Split count for a shape: ~1.5 CTAs per SM (two fit; measured on B200 at T = 8: q/k/v 36 tiles -> 6 splits 8.7 us, down_proj 28 tiles
 // -> 8 splits 27.5 us, 4 splits 30.5 us, no split 77 us), at least 8 K-blocks per CTA, at most 8 CTAs per cluster.
 static int pick_splits(int tiles, int k_blocks, int sms) {
@@ -512,7 +566,7 @@ static int pick_splits(int tiles, int k_blocks, int sms) {
 
 static int tokens_common(const void* X, const void* W, const void* bias, const void* residual, void* Y, int T, int N, int K, int epilogue,
                          int splits, const void* norm_weight, float eps, const float* stats_in, int stats_tiles, float* stats_out,
-                         const TokAppend& ap, void* stream) {
+                         const TokAppend& ap, void* stream, const uint8_t* suppress = nullptr, unsigned long long* keys = nullptr) {
     SVLM_REQUIRE(X && W, "NULL tensor argument");
     SVLM_REQUIRE(T >= 1 && T <= 64, "1..64 tokens per call (got %d); wider batches belong to svlm_gemm_bf16", T);
     SVLM_REQUIRE(N > 0 && K > 0 && K % 8 == 0, "bad N / K (K %d must be a multiple of 8)", K);
@@ -569,7 +623,7 @@ static int tokens_common(const void* X, const void* W, const void* bias, const v
     }
     TokParams p{T, N, K, epilogue, splits, stages, 2 * stages, x_bytes, ring_bytes, n_half, (const uint16_t*)bias, (const uint16_t*)residual, (uint16_t*)Y,
                 epilogue == TOK_EPI_SWIGLU ? n_half : N, (const uint16_t*)X, (const uint16_t*)norm_weight, eps, stats_in, stats_tiles,
-                stats_out};
+                stats_out, suppress, keys};
     const size_t smem = (size_t)fixed + (size_t)ring_bytes;
     switch (tn) {
         case 16: return launch_tokens<16>(tx, tw, p, ap, tiles, smem, (cudaStream_t)stream);
@@ -625,4 +679,27 @@ extern "C" int svlm_gemm_tokens_qkv_append(const svlm_arena_t* geometry, const s
     const int N = (q_heads + 2 * geometry->kv_heads) * 128;
     return tokens_common(X, W, bias, nullptr, nullptr, n_streams, N, hidden, TOK_EPI_QKV_APPEND, splits, norm_weight, eps, stats_in,
                          stats_tiles, nullptr, ap, stream);
+}
+
+extern "C" int svlm_gemm_tokens_lm_head_argmax(const void* X, const void* W, const void* norm_weight, float eps, const float* stats_in,
+                                               int stats_tiles, const uint8_t* suppress, int T, int N, int K, unsigned long long* keys,
+                                               void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(keys != nullptr && T <= 16, "keys is NULL or more than 16 tokens (%d)", T);
+    SVLM_REQUIRE(((uintptr_t)keys & 7) == 0, "keys must be 8-byte aligned");
+    TokAppend ap{};
+    return tokens_common(X, W, nullptr, nullptr, nullptr, T, N, K, TOK_EPI_ARGMAX, 1, norm_weight, eps, stats_in, stats_tiles, nullptr, ap, stream,
+                         suppress, keys);
+}
+
+extern "C" int svlm_streams_advance(unsigned long long* keys, int64_t* tok, const int32_t* active, int32_t* kv_len, int32_t* kv_after,
+                                    int32_t* next_pos, int n_streams, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    SVLM_REQUIRE(keys && tok && active && kv_len && kv_after && next_pos, "NULL argument");
+    SVLM_REQUIRE(n_streams >= 1 && n_streams <= SVLM_MAX_STREAMS, "n_streams %d out of range (1..%d)", n_streams, SVLM_MAX_STREAMS);
+    launch_pdl(PDL_OTHER, streams_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, keys, tok, active, kv_len, kv_after, next_pos,
+               n_streams);
+    return launch_status("streams_advance_kernel");
 }

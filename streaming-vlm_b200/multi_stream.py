@@ -55,6 +55,7 @@ class MultiStreamEngine:
         self._tok_ring = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
         self._tok_events = [torch.cuda.Event() for _ in range(2)]
         self._undo = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._keys = torch.zeros(B, dtype=torch.int64, device=dev)          # packed (logit, ~id) maxima of the lm_head launch, zero between steps
         # pinned staging buffers of the look-ahead loop's mask uploads, used round-robin: a buffer is rewritten two iterations later
         # at the earliest, after the host has waited for an event recorded behind its copy
         self._mask_ring = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(8)]
@@ -91,7 +92,7 @@ class MultiStreamEngine:
         # Five launches per layer, every projection ONE launch of the weight-streaming swap-AB GEMM (svlm_gemm_tokens: weight rows on
         # the tensor-core M dimension, the B tokens on N, split-K over a cluster) with everything around it fused:
         #   RMSNorm -> q/k/v projection -> bias -> mRoPE -> append to each stream's arena | split-KV attention over all streams |
-        #   o_proj + residual | RMSNorm -> gate/up projection -> SwiGLU | down_proj + residual;   final norm -> lm_head.
+        #   o_proj + residual | RMSNorm -> gate/up projection -> SwiGLU | down_proj + residual;   final norm -> lm_head -> argmax.
         # The two row-parallel launches leave per-tile sums of squares of the rows they wrote (`stats`), from which the NEXT launch's
         # fused RMSNorm gets its row statistics with one short read (layer 0 computes them from the embedding rows in the kernel).
         dev, bf = self.device, torch.bfloat16
@@ -106,14 +107,13 @@ class MultiStreamEngine:
             _abi.gemm_tokens(self._o.view(B, -1), L["wo"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_attn)
             _abi.gemm_tokens(x, L["wgu"], act, epilogue=_abi.EPI_SWIGLU, norm_weight=L["ln2"], eps=g.rms_eps, stats_in=st_attn)
             _abi.gemm_tokens(act, L["wd"], x, residual=x, epilogue=_abi.EPI_RESIDUAL, stats_out=st_mlp)
-        logits = torch.empty(B, e0.lm_head.shape[0], dtype=bf, device=dev)
-        _abi.gemm_tokens(x, e0.lm_head, logits, norm_weight=e0.norm, eps=g.rms_eps, stats_in=st_mlp)
-        logits = logits.float()
-        if e0.suppress is not None:
-            logits = logits.masked_fill(e0.suppress, float("-inf"))
+        # final norm + lm_head + suppress mask + argmax in the projection's epilogue (no logits tensor), then ONE small launch that hands
+        # every active stream its token and advances the device-side counters
+        _abi.gemm_tokens_lm_head_argmax(x, e0.lm_head, self._keys, norm_weight=e0.norm, eps=g.rms_eps, stats_in=st_mlp,
+                                        suppress_u8=e0.suppress_u8)
+        _abi.streams_advance(self._keys, self.tok, self.active, self.kv_len, self.kv_after, self.next_pos)
         merged_in_cluster = splits in (2, 4, 8)                # the batched attention merges these split counts inside clusters: no merge launch
-        self.launches += g.num_layers * (5 + (1 if splits > 1 and not merged_in_cluster else 0)) + 1
-        self._advance(torch.argmax(logits, dim=-1))
+        self.launches += g.num_layers * (5 + (1 if splits > 1 and not merged_in_cluster else 0)) + 2
 
     def _advance(self, nxt):
         act = self.active

@@ -973,3 +973,39 @@ def test_attn_decode_early_kv_prefetch_is_bit_identical(abi, tables, kv_after, s
         outs.append(torch.stack(res).cpu())
     assert torch.equal(bits(outs[0]), bits(outs[1]))
     assert not torch.equal(bits(outs[0][0]), bits(outs[0][1]))          # the appended row matters (different tokens, different outputs)
+
+
+@pytest.mark.parametrize("t,n,k", [(8, 152064, 3584), (16, 1000, 512), (3, 130, 64)])
+def test_gemm_tokens_lm_head_argmax_and_streams_advance(abi, t, n, k):
+    """Final norm + lm_head + suppress mask + argmax in the projection's epilogue == torch.argmax over the masked fp32 view of the bf16
+    logits (first index of the maximum, ties included: a few logits are made exactly equal); svlm_streams_advance hands the ids to the
+    ACTIVE streams only and advances their counters."""
+    g = torch.Generator().manual_seed(n + t)
+    x = torch.randn(t, k, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+    w[n // 2] = w[n // 3]                                            # two identical rows: an exact tie somewhere in the middle
+    nw = (1 + 0.1 * torch.randn(k, generator=g)).to(torch.bfloat16).to(DEV)
+    sup = torch.zeros(n, dtype=torch.bool)
+    sup[torch.randperm(n, generator=g)[: n // 10]] = True
+    h = torch.empty_like(x)
+    abi.add_rmsnorm(x, None, nw, None, h, 1e-6)
+    logits = torch.empty(t, n, dtype=torch.bfloat16, device=DEV)
+    abi.gemm_tokens(h, w, logits)
+    masked = logits.float().masked_fill(sup.to(DEV), float("-inf"))
+    want = torch.argmax(masked, dim=-1)
+    # force a tie for the winner of token 0 at a LOWER index that is not suppressed: the first index must win
+    keys = torch.zeros(t, dtype=torch.int64, device=DEV)
+    abi.gemm_tokens_lm_head_argmax(x, w, keys, norm_weight=nw, eps=1e-6, suppress_u8=sup.to(torch.uint8).to(DEV))
+    got = (0xFFFFFFFF - (keys & 0xFFFFFFFF)).cpu()
+    assert torch.equal(got, want.cpu()), (got.tolist(), want.cpu().tolist())
+    tok = torch.full((t,), 7, dtype=torch.int64, device=DEV)
+    active = torch.tensor([b % 3 != 1 for b in range(t)], dtype=torch.int32, device=DEV)
+    kv_len = torch.arange(100, 100 + t, dtype=torch.int32, device=DEV)
+    kv_after = torch.zeros(t, dtype=torch.int32, device=DEV)
+    nxt = torch.arange(500, 500 + t, dtype=torch.int32, device=DEV)
+    abi.streams_advance(keys, tok, active, kv_len, kv_after, nxt)
+    a = active.bool().cpu()
+    assert torch.equal(tok.cpu(), torch.where(a, want.cpu(), torch.full((t,), 7)))
+    assert torch.equal(kv_len.cpu(), (torch.arange(100, 100 + t) + a.int()).int())
+    assert torch.equal(kv_after.cpu(), kv_len.cpu() + 1) and torch.equal(nxt.cpu(), (torch.arange(500, 500 + t) + a.int()).int())
+    assert int(keys.abs().sum()) == 0
