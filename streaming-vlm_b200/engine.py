@@ -212,6 +212,7 @@ class StreamingEngine:
         self._early_kv = os.environ.get("SVLM_ATTN_EARLY_KV", "1") != "0"
         self._dec_o = torch.zeros(1, g.num_heads, g.head_dim, dtype=torch.bfloat16, device=dev)
         self._dec_act = torch.zeros(g.mlp, dtype=torch.bfloat16, device=dev)
+        self._dec_x = torch.zeros(g.hidden, dtype=torch.bfloat16, device=dev)
         self._dec_part = torch.zeros(g.hidden, dtype=torch.bfloat16, device=dev)
         self._argmax_key = torch.zeros(1, dtype=torch.int64, device=dev)
         self._pf_ids = torch.zeros(1024, dtype=torch.int64, device=dev)
@@ -596,7 +597,9 @@ class StreamingEngine:
         with SwiGLU -> down GEMV + residual; then final norm + lm_head GEMV + argmax + counter update."""
         c, g = self.cache, self.geo
         hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
-        x = F.embedding(self.tok_dev, self.embed)[0].contiguous()
+        x = self._dec_x                                 # embedding row of the token (own kernel: one launch instead of ATen's gather + copy)
+        _abi.embed_tokens(self.tok_dev, 1, self.embed, None, 0, x.view(1, -1), self._pf_status, VIDEO_PAD)
+        self.launches += 1
         q_rot, o, act = self._dec_q, self._dec_o, self._dec_act
         for li, L in enumerate(self.layers):
             _abi.gemv_qkv_rope_append(c.view, c.cur, li, L["wqkv"], x, L["ln1"], g.rms_eps, L["bqkv"], hq, q_rot, self.kv_len_dev,

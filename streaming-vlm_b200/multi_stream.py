@@ -86,7 +86,9 @@ class MultiStreamEngine:
         hq, hkv, d = g.num_heads, g.num_kv_heads, g.head_dim
         c0 = e0.cache
         before = e0.launches
-        x = F.embedding(self.tok, e0.embed)
+        x = torch.empty(B, g.hidden, dtype=torch.bfloat16, device=self.device)
+        _abi.embed_tokens(self.tok, B, e0.embed, None, 0, x, e0._pf_status)
+        self.launches += 1
         if not self.own_gemm:
             return self._decode_body_cublas(x, slots, splits, before)
         # Five launches per layer, every projection ONE launch of the weight-streaming swap-AB GEMM (svlm_gemm_tokens: weight rows on
